@@ -1,0 +1,173 @@
+/* b200npc.h -- C ABI of libb200npc.so, the sm_100a device library behind tenpy_b200.
+ *
+ * This is the drop-in boundary for the two-site-DMRG hot path of tenpy/tenpy.  Each entry point
+ * replaces one piece of the reference's native helper `tenpy/linalg/_npc_helper.pyx` (the only
+ * compiled component of the reference) or one LAPACK/BLAS call site of `tenpy/linalg/np_conserved.py`;
+ * the replaced reference code is cited next to each declaration as file:line (paths relative to the
+ * reference checkout, "pyx" = tenpy/linalg/_npc_helper.pyx, "npc" = tenpy/linalg/np_conserved.py).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success and a non-zero code on failure, with a
+ *     human readable message available from b200_last_error() (thread local).
+ *   - pointers named *_dev / A / B / C / X / Y point to DEVICE memory (HBM) of the current CUDA device;
+ *     pointers named *_host (and all plan-construction inputs) point to HOST memory.
+ *   - all floating point data is IEEE binary64 ("f64"); all indices/offsets are int64 counted in
+ *     ELEMENTS (not bytes) relative to the base pointer of a packed block buffer.
+ *   - a "packed block buffer" holds all stored blocks of one Array back to back, each block C-contiguous
+ *     (row-major), block starts aligned to B200_BLOCK_ALIGN elements, padding zero-filled.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - no function falls back to the CPU: without a CUDA device they fail with B200_ERR_CUDA.
+ */
+#ifndef B200NPC_H
+#define B200NPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+#define B200_BLOCK_ALIGN 16 /* elements (=128 bytes) */
+
+#define B200_OK 0
+#define B200_ERR_ARG 1
+#define B200_ERR_CUDA 2
+#define B200_ERR_NOCONV 3
+#define B200_ERR_ALLOC 4
+
+typedef void *b200_stream_t;
+
+/* ---- library / device ------------------------------------------------------------------------- */
+int b200_abi_version(void);
+const char *b200_last_error(void);
+/* number of visible CUDA devices (0 if none / no driver) */
+int b200_device_count(void);
+/* properties of device `dev`: SM count, compute capability, total memory */
+int b200_device_info(int dev, int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes);
+/* self test of the FP64 tensor-core fragment layouts used by the kernels; out_host[0..3] receive the max
+ * abs error of (m16n8k8 path, m8n8k4 path, grouped gemm 128-tile, grouped gemm 64-tile) on a fixed problem */
+int b200_selftest(double *out_host);
+
+/* ---- host-side integer bookkeeping (no device needed) ------------------------------------------- */
+/* indices where consecutive rows of a row-major (n x width) int64 table differ, incl. 0 and n.
+ * replaces charges._find_row_differences, charges.py:1922 / pyx:635.  out_host has room for n+1. */
+int b200_find_row_differences(const int64_t *rows_host, int64_t n, int64_t width, int64_t *out_host,
+                              int64_t *n_out);
+/* argsort of the rows, LAST column is the primary key (np.lexsort(rows.T)); stable.
+ * replaces the np.lexsort calls of pyx:1357-1377 (_tensordot_pre_sort) and npc:1441. */
+int b200_lexsort_rows(const int64_t *rows_host, int64_t n, int64_t width, int64_t *perm_host);
+/* charges modulo `mod` in place (mod==1: untouched). replaces ChargeInfo.make_valid charges.py:267/pyx:478 */
+int b200_make_valid(int64_t *charges_host, int64_t n, int64_t qnumber, const int64_t *mod_host);
+/* block index map: out[j] = i repeated blocksizes[i] times. replaces charges._map_blocks :1945/pyx:732 */
+int b200_map_blocks(const int64_t *blocksizes_host, int64_t n, int64_t *out_host);
+
+/* ---- tensordot: contraction plan + grouped GEMM --------------------------------------------------- */
+/* A contraction plan is the host-precomputed charge-sector bookkeeping of one npc.tensordot
+ * (replaces _tensordot_pre_sort pyx:1337, _tensordot_match_charges pyx:1382 and the packing loop
+ * pyx:1710-1754 that fills CblasGemmBatch pyx:151).  Inputs describe the stored blocks of
+ *   a: (n_a x rank_a) qindex table, contracted legs are the LAST n_contr columns, block i is a row-major
+ *      (a_rows[i] x a_cols[i]) matrix at element offset a_off[i];
+ *   b: (n_b x rank_b) qindex table, contracted legs are the FIRST n_contr columns, block j is a row-major
+ *      (b_rows[j] x b_cols[j]) matrix at element offset b_off[j].
+ * Output blocks C[r,c] = sum_k A[r,k] B[k,c] exist for every (row group r of a, column group c of b) with
+ * at least one common contracted qindex tuple; they are lex-sorted like the reference (pyx:1772-1778). */
+typedef struct b200_tdot_plan b200_tdot_plan;
+int b200_tdot_plan_create(const int64_t *a_qdata_host, int64_t n_a, int32_t rank_a,
+                          const int64_t *b_qdata_host, int64_t n_b, int32_t rank_b, int32_t n_contr,
+                          const int64_t *a_rows_host, const int64_t *a_cols_host, const int64_t *a_off_host,
+                          const int64_t *b_rows_host, const int64_t *b_cols_host, const int64_t *b_off_host,
+                          b200_tdot_plan **plan_out);
+/* sizes: number of C blocks, number of block products (GEMMs), C buffer size in elements, flops = sum 2mkn */
+int b200_tdot_plan_info(const b200_tdot_plan *plan, int64_t *n_c, int64_t *n_pairs, int64_t *c_size,
+                        double *flops);
+/* fetch the result block table: c_qdata (n_c x (rank_a + rank_b - 2 n_contr)), offsets, rows, cols */
+int b200_tdot_plan_get(const b200_tdot_plan *plan, int64_t *c_qdata_host, int64_t *c_off_host,
+                       int64_t *c_rows_host, int64_t *c_cols_host);
+/* fetch the block-product list (the list the reference hands to CblasGemmBatch, pyx:1743): for output block
+ * t the products are p in [pair_ptr[t], pair_ptr[t+1]); pair_ptr has n_c+1 entries, the others n_pairs. */
+int b200_tdot_plan_pairs(const b200_tdot_plan *plan, int64_t *pair_ptr_host, int64_t *a_off_host,
+                         int64_t *b_off_host, int64_t *k_host);
+/* execute: C = A . B for all blocks; C must hold c_size elements (padding is written as zero-free: the
+ * caller zero-fills C once if it needs zero padding).  replaces CblasGemmBatch.run pyx:204-274. */
+int b200_tdot_plan_run(b200_tdot_plan *plan, const double *A, const double *B, double *C,
+                       b200_stream_t stream);
+void b200_tdot_plan_destroy(b200_tdot_plan *plan);
+
+/* Raw grouped GEMM without a plan object (used by the host-buffer plugin path and the benchmark):
+ * n_tasks output blocks; task t is C_t (m[t] x n[t], row-major, at c_off[t]) = sum over pairs
+ * p in [pair_ptr[t], pair_ptr[t+1]) of A_p (m[t] x k[p] at a_off[p]) . B_p (k[p] x n[t] at b_off[p]). */
+int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m_host, const int64_t *n_host,
+                          const int64_t *c_off_host, const int64_t *pair_ptr_host, int64_t n_pairs,
+                          const int64_t *k_host, const int64_t *a_off_host, const int64_t *b_off_host,
+                          const double *A, const double *B, double *C, b200_stream_t stream);
+
+/* ---- BLAS-1 on packed block buffers (Lanczos vector ops) ------------------------------------------ */
+/* y += alpha x.  replaces Array.iadd_prefactor_other npc:2373 / pyx:860 (daxpy pyx:328-335) */
+int b200_axpy_f64(int64_t n, double alpha, const double *X, double *Y, b200_stream_t stream);
+/* x *= alpha.  replaces Array.iscale_prefactor npc:2386 / pyx:964 (dscal pyx:350-363) */
+int b200_scal_f64(int64_t n, double alpha, double *X, b200_stream_t stream);
+/* out_dev[0] = sum x_i y_i (deterministic two-stage reduction).  scratch_dev: >= B200_DOT_SCRATCH doubles.
+ * replaces _inner_worker pyx:1791 (ddot pyx:1854-1871) and Array.norm npc:2241 (with X == Y). */
+#define B200_DOT_SCRATCH 2048
+int b200_dot_f64(int64_t n, const double *X, const double *Y, double *scratch_dev, double *out_dev,
+                 b200_stream_t stream);
+/* segment versions for Arrays with different block tables: seg_dev holds n_seg triples
+ * (x_off, y_off, len) as int64 in device memory. */
+int b200_axpy_segments_f64(int64_t n_seg, const int64_t *seg_dev, int64_t max_len, double alpha,
+                           const double *X, double *Y, b200_stream_t stream);
+int b200_dot_segments_f64(int64_t n_seg, const int64_t *seg_dev, int64_t max_len, const double *X,
+                          const double *Y, double *scratch_dev, double *out_dev, b200_stream_t stream);
+/* fused Lanczos step: w -= alpha*v1 + beta*v0 and out_dev[0] = |w|^2 in one pass (v0 may be NULL).
+ * replaces the two iadd_prefactor_other + norm calls of krylov_based.py:665-671 */
+int b200_lanczos_update_f64(int64_t n, double alpha, const double *V1, double beta, const double *V0,
+                            double *W, double *scratch_dev, double *out_dev, b200_stream_t stream);
+
+/* ---- block data movement ------------------------------------------------------------------------- */
+/* Strided N-d block copies: dst[doff + sum_i idx_i*dstride_i] = src[soff + sum_i idx_i*sstride_i].
+ * task_dev holds n_tasks records of B200_COPY_REC int64: [soff, doff, n_elem, rank, shape[6], sstride[6],
+ * dstride[6]] (iteration order = row-major over `shape`; make dstride the contiguous one for coalescing).
+ * replaces _sliced_copy charges.py:1956/pyx:754, Array_itranspose pyx:813 (+ _imake_contiguous pyx:1000),
+ * _combine_legs_worker pyx:1013, _split_legs_worker pyx:1136. */
+#define B200_COPY_REC 22
+#define B200_COPY_MAXRANK 6
+int b200_copy_blocks_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t *task_host,
+                         const double *SRC, double *DST, b200_stream_t stream);
+/* take along one axis: dst[o, j, i] = src[o, idx[j], i]; records of 7 int64:
+ * [soff, doff, outer, n_keep, inner, src_len, idx_off]; idx_dev int64 index pool.
+ * replaces Array.iproject npc:1914 (np.compress per block). */
+#define B200_TAKE_REC 7
+int b200_take_blocks_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t *task_host,
+                         const int64_t *idx_dev, const double *SRC, double *DST, b200_stream_t stream);
+/* x[o, j, i] *= s[s_off + j]; records of 5 int64: [off, outer, len, inner, s_off].
+ * replaces Array.iscale_axis npc:2108. */
+#define B200_SCALE_REC 5
+int b200_scale_axis_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t *task_host,
+                        const double *S_dev, double *X, b200_stream_t stream);
+
+/* ---- block-diagonal SVD / eigh ------------------------------------------------------------------- */
+/* Batched one-sided block-Jacobi SVD of nblocks independent row-major matrices A_i (m[i] x n[i]) at
+ * a_off[i]: A_i = U_i diag(S_i) VT_i with k_i = min(m_i, n_i), S_i sorted descending,
+ * U_i (m_i x k_i) at u_off[i], S_i at s_off[i], VT_i (k_i x n_i) at vt_off[i], all row-major.
+ * A is not modified.  work_dev must hold b200_block_svd_worksize(...) bytes.  Synchronous on `stream`.
+ * info_host[i] = number of Jacobi sweeps used (>0) or -1 if not converged.
+ * replaces _svd_worker npc:4950 -> svd_robust.svd svd_robust.py:37 (LAPACK gesdd / gesvd). */
+int64_t b200_block_svd_worksize(int64_t nblocks, const int64_t *m_host, const int64_t *n_host);
+int b200_block_svd_f64(int64_t nblocks, const int64_t *m_host, const int64_t *n_host,
+                       const int64_t *a_off_host, const int64_t *u_off_host, const int64_t *s_off_host,
+                       const int64_t *vt_off_host, const double *A, double *U, double *S, double *VT,
+                       void *work_dev, int64_t work_bytes, int32_t *info_host, b200_stream_t stream);
+/* Batched symmetric eigen-decomposition of nblocks row-major symmetric matrices A_i (n[i] x n[i]):
+ * A_i = V_i diag(W_i) V_i^T, W_i ascending, eigenvectors in the COLUMNS of V_i (row-major n x n).
+ * replaces _eig_worker npc:5041 (np.linalg.eigh, LAPACK syevd). */
+int64_t b200_block_eigh_worksize(int64_t nblocks, const int64_t *n_host);
+int b200_block_eigh_f64(int64_t nblocks, const int64_t *n_host, const int64_t *a_off_host,
+                        const int64_t *w_off_host, const int64_t *v_off_host, const double *A, double *W,
+                        double *V, void *work_dev, int64_t work_bytes, int32_t *info_host,
+                        b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NPC_H */

@@ -1,0 +1,77 @@
+"""Device plumbing: the library handle, HBM buffers (torch tensors used as plain device memory) and
+host<->device copies.  No arithmetic happens here and none happens through torch ops: every floating
+point operation on the hot path is a kernel of ``libb200npc.so`` reached through :mod:`tenpy_b200._lib`.
+"""
+# Copyright (C) 2026 tenpy_b200 authors. Apache-2.0.
+
+import numpy as np
+import torch
+
+from ._lib import DeviceLib, B200Error, DOT_SCRATCH
+
+__all__ = ['get_lib', 'use_library', 'empty', 'zeros', 'to_device', 'to_host', 'scalar_out', 'read_scalar',
+           'B200Error']
+
+_state = {'lib': None, 'scratch': None, 'out': None}
+
+
+def get_lib():
+    """Return the process-wide :class:`DeviceLib`; loads ``libb200npc.so`` on first use.
+
+    Raises :class:`B200Error` when the extension is not built or no GPU is visible (no CPU fallback)."""
+    lib = _state['lib']
+    if lib is None:
+        lib = _state['lib'] = DeviceLib()
+    return lib
+
+
+def use_library(lib):
+    """Install an already constructed library object (e.g. bound to another device)."""
+    _state['lib'] = lib
+    _state['scratch'] = None
+    _state['out'] = None
+    return lib
+
+
+def device():
+    return get_lib().device
+
+
+def empty(n):
+    return torch.empty(int(n), dtype=torch.float64, device=get_lib().device)
+
+
+def zeros(n):
+    return torch.zeros(int(n), dtype=torch.float64, device=get_lib().device)
+
+
+def to_device(a, pin=False):
+    """numpy array (float64 / int64 / int32) -> device tensor."""
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a)
+    dev = get_lib().device
+    if dev.type == 'cpu':
+        return t.clone()
+    return t.to(dev)
+
+
+def to_host(t):
+    """device tensor -> numpy array (synchronises)."""
+    return t.detach().cpu().numpy()
+
+
+def dot_scratch():
+    if _state['scratch'] is None:
+        _state['scratch'] = empty(DOT_SCRATCH)
+    return _state['scratch']
+
+
+def scalar_out():
+    if _state['out'] is None:
+        _state['out'] = empty(8)
+    return _state['out']
+
+
+def read_scalar(t):
+    """read element 0 of a device tensor (synchronises the stream)."""
+    return float(t[:1].cpu().numpy()[0])

@@ -1,0 +1,668 @@
+// svd.cu -- batched block-diagonal SVD and symmetric eigen-decomposition by one-sided block Jacobi.
+//
+// Replaces, for the B200, the per-charge-block LAPACK calls of the reference:
+//   npc._svd_worker (tenpy/linalg/np_conserved.py:4950) -> svd_robust.svd (svd_robust.py:37, gesdd/gesvd)
+//   npc._eig_worker (np_conserved.py:5041)              -> np.linalg.eigh (syevd)
+//
+// Algorithm (all blocks of one Array in one batch):
+//   Each matrix is held as Y (q x p, q <= p, row-major, rows = the vectors to orthogonalise; Y = A or A^T)
+//   plus W (q x q) = accumulated orthogonal row transformation, W Y0 = Y.  Rows are grouped in blocks of
+//   JB = 16.  One Jacobi *round* processes nb/2 disjoint block pairs (round-robin tournament); one CTA
+//   owns one pair = a 32-row panel P:
+//     1. G = P P^T (32x32) streamed through shared memory with FP64 tensor-core MMAs,
+//     2. G = Q L Q^T by a parallel cyclic two-sided Jacobi in shared memory,
+//     3. P <- Q^T P and the same rows of W <- Q^T W (second streamed pass, DMMA).
+//   A pair whose scaled off-diagonal max |g_ij|/sqrt(g_ii g_jj) is below tol is left untouched; a matrix
+//   is converged once a full cycle of rounds touched nothing.  Singular values = row norms of Y,
+//   sorted on the host (k doubles), vectors written by a final gather kernel.
+// Never produces NaN for finite input (the reference falls back gesdd->gesvd for that, npc:4971-4978).
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int JB = 16;          // rows per block
+constexpr int JP = 2 * JB;      // rows per panel
+constexpr int JKC = 128;        // streamed chunk (columns)
+constexpr int JLDP = JKC + 4;   // smem row stride of a panel chunk
+constexpr int JTHREADS = 256;
+constexpr int JLDG = JP + 1;
+constexpr int JLDQT = JP + 4;
+constexpr int J_INNER_SWEEPS = 12;
+
+struct JMat {
+    int64_t y_off, w_off, snorm_off;       // element offsets into the f64 work area
+    int64_t a_off, u_off, s_off, vt_off;   // element offsets into the caller's buffers
+    int32_t m, n;                          // original shape
+    int32_t q, p;                          // vectors, vector length
+    int32_t qp, nb;                        // padded vector count (= nb*JB), number of row blocks (even)
+    int32_t ldy, ldw;
+    int32_t transposed;                    // Y = A^T
+    int32_t cta_begin;                     // first CTA of this matrix in a round launch
+    int32_t perm_off;                      // offset into the int32 permutation pool
+    int32_t pad;
+    double shift;                          // eigh: diagonal shift
+};
+
+constexpr int jacobi_smem_bytes() {
+    return (2 * JP * JLDP + 2 * JP * JLDG + JP * JLDQT) * (int)sizeof(double) + 256;
+}
+
+__device__ __forceinline__ void j_load_chunk(double *sP, const double *base, int ld, int rowA0, int rowB0, int col0,
+                                             int tid) {
+    constexpr int CH = JP * (JKC / 2);
+#pragma unroll
+    for (int c = tid; c < CH; c += JTHREADS) {
+        int r = c / (JKC / 2), cc = (c % (JKC / 2)) * 2;
+        int grow = r < JB ? rowA0 + r : rowB0 + r - JB;
+        int gcol = col0 + cc;
+        bool ok = gcol < ld;
+        const double *src = ok ? base + (int64_t)grow * ld + gcol : base;
+        cp_async16(sP + r * JLDP + cc, src, ok ? 16 : 0);
+    }
+}
+
+// rows of `base` (ld) <- Q^T rows ; panel rows rowA0.., rowB0..
+__device__ __forceinline__ void j_apply(double *bufs, const double (&qa)[2][4][4], double *base, int ld, int rowA0,
+                                        int rowB0, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int nch = (ld + JKC - 1) / JKC;
+    j_load_chunk(bufs, base, ld, rowA0, rowB0, 0, tid);
+    cp_async_commit();
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, base, ld, rowA0, rowB0, (ch + 1) * JKC, tid);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double *sp = bufs + (ch & 1) * JP * JLDP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int nt = warp * 2 + h;
+            const int col = ch * JKC + nt * 8;
+            if (col < ld) {
+                double acc[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[i][e] = 0.0;
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8) {
+                    double bf[2];
+                    bf[0] = sp[(k8 * 8 + t) * JLDP + nt * 8 + g];
+                    bf[1] = sp[(k8 * 8 + t + 4) * JLDP + nt * 8 + g];
+                    dmma_16x8x8(acc[0], qa[0][k8], bf);
+                    dmma_16x8x8(acc[1], qa[1][k8], bf);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        int pr = i * 16 + g + 8 * hh;
+                        int grow = pr < JB ? rowA0 + pr : rowB0 + pr - JB;
+                        double *dst = base + (int64_t)grow * ld + col + 2 * t;
+                        *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][2 * hh], acc[i][2 * hh + 1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_round_kernel(double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
+                        int round, int *__restrict__ rot_count, const int *__restrict__ done, double tol_scale) {
+    extern __shared__ __align__(16) double jsmem[];
+    double *bufs = jsmem;                    // 2 * JP * JLDP
+    double *sG = bufs + 2 * JP * JLDP;       // JP * JLDG
+    double *sQ = sG + JP * JLDG;             // JP * JLDG
+    double *sQT = sQ + JP * JLDG;            // JP * JLDQT
+    __shared__ double cs_c[JB], cs_s[JB];
+    __shared__ int pr_p[JB], pr_q[JB];
+    __shared__ double red[32];
+
+    const int mi = cta_mat[blockIdx.x];
+    if (done[mi]) return;
+    const JMat mt = mats[mi];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int j = blockIdx.x - mt.cta_begin;
+    const int nb = mt.nb;
+    int ba, bb;
+    {
+        const int nr = nb - 1;
+        const int r = round % nr;
+        if (j == 0) {
+            ba = nb - 1;
+            bb = r;
+        } else {
+            ba = (r + j) % nr;
+            bb = (r - j + nr) % nr;
+        }
+        if (ba > bb) {
+            int tmp = ba;
+            ba = bb;
+            bb = tmp;
+        }
+    }
+    const int rowA0 = ba * JB, rowB0 = bb * JB;
+    double *Y = work + mt.y_off;
+    double *W = work + mt.w_off;
+    const int ld = mt.ldy;
+
+    // ---- phase 1: G = P P^T ----
+    {
+        const int tm = warp >> 2, tn = warp & 3;  // 2 x 4 tiles of 16 x 8
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const int nch = (ld + JKC - 1) / JKC;
+        j_load_chunk(bufs, Y, ld, rowA0, rowB0, 0, tid);
+        cp_async_commit();
+        for (int ch = 0; ch < nch; ++ch) {
+            if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, Y, ld, rowA0, rowB0, (ch + 1) * JKC, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            const double *sp = bufs + (ch & 1) * JP * JLDP;
+#pragma unroll
+            for (int k8 = 0; k8 < JKC / 8; ++k8) {
+                double af[4], bf[2];
+                const double *ap = sp + (tm * 16 + g) * JLDP + k8 * 8 + t;
+                af[0] = ap[0];
+                af[1] = ap[8 * JLDP];
+                af[2] = ap[4];
+                af[3] = ap[8 * JLDP + 4];
+                const double *bp = sp + (tn * 8 + g) * JLDP + k8 * 8 + t;
+                bf[0] = bp[0];
+                bf[1] = bp[4];
+                dmma_16x8x8(acc, af, bf);
+            }
+            __syncthreads();
+        }
+        cp_async_wait<0>();
+        const int r0 = tm * 16 + g, c0 = tn * 8 + 2 * t;
+        sG[r0 * JLDG + c0] = acc[0];
+        sG[r0 * JLDG + c0 + 1] = acc[1];
+        sG[(r0 + 8) * JLDG + c0] = acc[2];
+        sG[(r0 + 8) * JLDG + c0 + 1] = acc[3];
+    }
+    __syncthreads();
+
+    // ---- convergence measure of this pair ----
+    double offmax = 0.0;
+    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+        int r = idx / JP, c = idx % JP;
+        if (r < c) {
+            double d = sG[r * JLDG + r] * sG[c * JLDG + c];
+            double o = fabs(sG[r * JLDG + c]);
+            if (d > 0.0) {
+                double v = o / sqrt(d);
+                offmax = fmax(offmax, v);
+            }
+        }
+    }
+    offmax = warp_max(offmax);
+    if (lane == 0) red[warp] = offmax;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int w = 0; w < JTHREADS / 32; ++w) v = fmax(v, red[w]);
+        red[0] = v;
+    }
+    __syncthreads();
+    offmax = red[0];
+    const double tol = tol_scale * sqrt((double)mt.p);
+    if (!(offmax > tol)) return;  // uniform for the whole CTA
+    if (tid == 0) atomicAdd(&rot_count[mi], 1);
+
+    // ---- phase 2: G = Q L Q^T by parallel cyclic Jacobi ----
+    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+        int r = idx / JP, c = idx % JP;
+        sQ[r * JLDG + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const double tol_in = 1e-15;
+    for (int sweep = 0; sweep < J_INNER_SWEEPS; ++sweep) {
+        int any = 0;
+        for (int step = 0; step < JP - 1; ++step) {
+            if (tid < JB) {
+                int a, b;
+                if (tid == 0) {
+                    a = JP - 1;
+                    b = step;
+                } else {
+                    a = (step + tid) % (JP - 1);
+                    b = (step - tid + (JP - 1)) % (JP - 1);
+                }
+                int p = a < b ? a : b, q = a < b ? b : a;
+                double gpp = sG[p * JLDG + p], gqq = sG[q * JLDG + q], gpq = sG[p * JLDG + q];
+                double c = 1.0, s = 0.0;
+                double lim = tol_in * sqrt(fabs(gpp * gqq));
+                if (fabs(gpq) > lim && fabs(gpq) > 0.0) {
+                    double tau = (gqq - gpp) / (2.0 * gpq);
+                    double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c = 1.0 / sqrt(1.0 + tt * tt);
+                    s = tt * c;
+                    any = 1;
+                }
+                pr_p[tid] = p;
+                pr_q[tid] = q;
+                cs_c[tid] = c;
+                cs_s[tid] = s;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < JB * JP; idx += JTHREADS) {  // rows
+                int jj = idx / JP, col = idx % JP;
+                int p = pr_p[jj], q = pr_q[jj];
+                double c = cs_c[jj], s = cs_s[jj];
+                double gp = sG[p * JLDG + col], gq = sG[q * JLDG + col];
+                sG[p * JLDG + col] = c * gp - s * gq;
+                sG[q * JLDG + col] = s * gp + c * gq;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < JB * JP; idx += JTHREADS) {  // columns of G and Q
+                int jj = idx / JP, row = idx % JP;
+                int p = pr_p[jj], q = pr_q[jj];
+                double c = cs_c[jj], s = cs_s[jj];
+                double gp = sG[row * JLDG + p], gq = sG[row * JLDG + q];
+                sG[row * JLDG + p] = c * gp - s * gq;
+                sG[row * JLDG + q] = s * gp + c * gq;
+                double qp_ = sQ[row * JLDG + p], qq_ = sQ[row * JLDG + q];
+                sQ[row * JLDG + p] = c * qp_ - s * qq_;
+                sQ[row * JLDG + q] = s * qp_ + c * qq_;
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(any)) break;
+    }
+    // order the new rows by descending eigenvalue (norm^2): helps the outer convergence (de Rijk)
+    // rank[i] = number of entries with larger diagonal (ties by index)
+    if (tid < JP) {
+        double di = sG[tid * JLDG + tid];
+        int rk = 0;
+        for (int k = 0; k < JP; ++k) {
+            double dk = sG[k * JLDG + k];
+            if (dk > di || (dk == di && k < tid)) ++rk;
+        }
+        // store rank in sG's unused padding column
+        sG[tid * JLDG + JP] = (double)rk;
+    }
+    __syncthreads();
+    // sQT[rank(i)][k] = Q[k][i]   (row `rank(i)` of Q^T, sorted)
+    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+        int i = idx / JP, k = idx % JP;
+        int rk = (int)sG[i * JLDG + JP];
+        sQT[rk * JLDQT + k] = sQ[k * JLDG + i];
+    }
+    __syncthreads();
+
+    // ---- phase 3: P <- Q^T P, W rows <- Q^T W rows ----
+    double qa[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+            const double *ap = sQT + (i * 16 + g) * JLDQT + k8 * 8 + t;
+            qa[i][k8][0] = ap[0];
+            qa[i][k8][1] = ap[8 * JLDQT];
+            qa[i][k8][2] = ap[4];
+            qa[i][k8][3] = ap[8 * JLDQT + 4];
+        }
+    j_apply(bufs, qa, Y, ld, rowA0, rowB0, tid);
+    j_apply(bufs, qa, W, mt.ldw, rowA0, rowB0, tid);
+}
+
+// ---- init / finalize kernels ---------------------------------------------------------------------
+// SVD init: Y = A or A^T (zero padded), W = identity.  grid (chunks, nmat)
+__global__ void __launch_bounds__(256) svd_init_kernel(double *__restrict__ work, const JMat *__restrict__ mats,
+                                                       const double *__restrict__ A) {
+    const JMat mt = mats[blockIdx.y];
+    double *Y = work + mt.y_off;
+    double *W = work + mt.w_off;
+    const double *a = A + mt.a_off;
+    const int64_t ny = (int64_t)mt.q * mt.p;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ny; e += stride) {
+        int r = (int)(e / mt.p), c = (int)(e % mt.p);
+        double v = mt.transposed ? a[(int64_t)c * mt.n + r] : a[(int64_t)r * mt.n + c];
+        Y[(int64_t)r * mt.ldy + c] = v;
+    }
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mt.qp; e += stride)
+        W[e * mt.ldw + e] = 1.0;
+}
+
+// eigh init: Y = A + shift*I.  shift[mat] was computed by eigh_shift_kernel.
+__global__ void __launch_bounds__(256) eigh_shift_kernel(JMat *__restrict__ mats, const double *__restrict__ A) {
+    __shared__ double red[32];
+    JMat *mt = mats + blockIdx.x;
+    const double *a = A + mt->a_off;
+    const int64_t nn = (int64_t)mt->n * mt->n;
+    double s = 0.0;
+    for (int64_t e = threadIdx.x; e < nn; e += blockDim.x) s = fma(a[e], a[e], s);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) mt->shift = 1.0625 * sqrt(s) + 1e-300;
+}
+
+__global__ void __launch_bounds__(256) eigh_init_kernel(double *__restrict__ work, const JMat *__restrict__ mats,
+                                                        const double *__restrict__ A) {
+    const JMat mt = mats[blockIdx.y];
+    double *Y = work + mt.y_off;
+    double *W = work + mt.w_off;
+    const double *a = A + mt.a_off;
+    const int64_t ny = (int64_t)mt.q * mt.p;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ny; e += stride) {
+        int r = (int)(e / mt.p), c = (int)(e % mt.p);
+        // symmetrise (use both triangles) like a Hermitian solver would see one triangle
+        double v = 0.5 * (a[(int64_t)r * mt.n + c] + a[(int64_t)c * mt.n + r]);
+        if (r == c) v += mt.shift;
+        Y[(int64_t)r * mt.ldy + c] = v;
+    }
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mt.qp; e += stride)
+        W[e * mt.ldw + e] = 1.0;
+}
+
+// row norms of Y: grid (max_q, nmat), 128 threads
+__global__ void __launch_bounds__(128) jacobi_norms_kernel(double *__restrict__ work, const JMat *__restrict__ mats) {
+    __shared__ double red[32];
+    const JMat mt = mats[blockIdx.y];
+    const int r = blockIdx.x;
+    if (r >= mt.q) return;
+    const double *y = work + mt.y_off + (int64_t)r * mt.ldy;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < mt.p; c += blockDim.x) s = fma(y[c], y[c], s);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) work[mt.snorm_off + r] = sqrt(s);
+}
+
+// SVD finalize: grid (max_k, nmat)
+__global__ void __launch_bounds__(128)
+    svd_finalize_kernel(const double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ perm,
+                        double *__restrict__ U, double *__restrict__ S, double *__restrict__ VT) {
+    const JMat mt = mats[blockIdx.y];
+    const int r = blockIdx.x;
+    const int k = mt.q;
+    if (r >= k) return;
+    const int src = perm[mt.perm_off + r];
+    const double s = work[mt.snorm_off + src];
+    const double inv = s > 0.0 ? 1.0 / s : 0.0;
+    const double *y = work + mt.y_off + (int64_t)src * mt.ldy;
+    const double *w = work + mt.w_off + (int64_t)src * mt.ldw;
+    if (threadIdx.x == 0) S[mt.s_off + r] = s;
+    double *u = U + mt.u_off;
+    double *vt = VT + mt.vt_off;
+    if (mt.transposed) {  // Y rows: length m -> U[:, r];  W rows: length n -> VT[r, :]
+        for (int i = threadIdx.x; i < mt.m; i += blockDim.x) u[(int64_t)i * k + r] = y[i] * inv;
+        for (int c = threadIdx.x; c < mt.n; c += blockDim.x) vt[(int64_t)r * mt.n + c] = w[c];
+    } else {  // Y rows: length n -> VT[r, :];  W rows: length m -> U[:, r]
+        for (int c = threadIdx.x; c < mt.n; c += blockDim.x) vt[(int64_t)r * mt.n + c] = y[c] * inv;
+        for (int i = threadIdx.x; i < mt.m; i += blockDim.x) u[(int64_t)i * k + r] = w[i];
+    }
+}
+
+// eigh finalize: eigenvalue r (ascending) = norm[perm[r]] - shift; V[:, r] = W[perm[r], :]
+__global__ void __launch_bounds__(128)
+    eigh_finalize_kernel(const double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ perm,
+                         double *__restrict__ Wout, double *__restrict__ V) {
+    const JMat mt = mats[blockIdx.y];
+    const int r = blockIdx.x;
+    const int n = mt.n;
+    if (r >= n) return;
+    const int src = perm[mt.perm_off + r];
+    const double *w = work + mt.w_off + (int64_t)src * mt.ldw;
+    if (threadIdx.x == 0) Wout[mt.s_off + r] = work[mt.snorm_off + src] - mt.shift;
+    double *v = V + mt.vt_off;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[(int64_t)i * n + r] = w[i];
+}
+
+// ---- host driver -----------------------------------------------------------------------------------
+struct JLayout {
+    std::vector<JMat> mats;
+    std::vector<int> cta_mat;
+    int64_t f64_elems = 0;     // doubles in the work area
+    int64_t perm_elems = 0;
+    int max_q = 0, max_nb = 0;
+    // byte offsets of the integer regions inside the work buffer
+    int64_t off_mats = 0, off_cta = 0, off_rot = 0, off_done = 0, off_perm = 0, total_bytes = 0;
+};
+
+static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, bool eigh, JLayout &L) {
+    L.mats.resize((size_t)nblocks);
+    int64_t off = 0;
+    int cta = 0;
+    int64_t perm = 0;
+    for (int64_t i = 0; i < nblocks; ++i) {
+        JMat &mt = L.mats[(size_t)i];
+        memset(&mt, 0, sizeof(JMat));
+        mt.m = (int32_t)m[i];
+        mt.n = (int32_t)(eigh ? m[i] : n[i]);
+        mt.transposed = (!eigh && mt.m >= mt.n) ? 1 : 0;
+        mt.q = std::min(mt.m, mt.n);
+        mt.p = std::max(mt.m, mt.n);
+        int nb = (int)((mt.q + JB - 1) / JB);
+        if (nb < 2) nb = 2;
+        if (nb & 1) ++nb;
+        mt.nb = nb;
+        mt.qp = nb * JB;
+        mt.ldy = (int32_t)rup(mt.p, 16);
+        mt.ldw = (int32_t)rup(mt.qp, 16);
+        mt.y_off = off;
+        off += (int64_t)mt.qp * mt.ldy;
+        mt.w_off = off;
+        off += (int64_t)mt.qp * mt.ldw;
+        mt.snorm_off = off;
+        off += rup(mt.qp, 16);
+        mt.cta_begin = cta;
+        for (int c = 0; c < nb / 2; ++c) L.cta_mat.push_back((int)i);
+        cta += nb / 2;
+        mt.perm_off = (int32_t)perm;
+        perm += mt.q;
+        L.max_q = std::max(L.max_q, (int)mt.q);
+        L.max_nb = std::max(L.max_nb, nb);
+    }
+    L.f64_elems = off;
+    L.perm_elems = perm;
+    int64_t b = rup(off * (int64_t)sizeof(double), 256);
+    L.off_mats = b;
+    b += rup((int64_t)nblocks * (int64_t)sizeof(JMat), 256);
+    L.off_cta = b;
+    b += rup((int64_t)L.cta_mat.size() * 4, 256);
+    L.off_rot = b;
+    b += rup(nblocks * 4, 256);
+    L.off_done = b;
+    b += rup(nblocks * 4, 256);
+    L.off_perm = b;
+    b += rup(perm * 4 + 4, 256);
+    L.total_bytes = b;
+}
+
+static int run_jacobi(const JLayout &L, char *work, cudaStream_t st, int32_t *info, int max_sweeps) {
+    const int nmat = (int)L.mats.size();
+    double *wf = reinterpret_cast<double *>(work);
+    JMat *d_mats = reinterpret_cast<JMat *>(work + L.off_mats);
+    int *d_cta = reinterpret_cast<int *>(work + L.off_cta);
+    int *d_rot = reinterpret_cast<int *>(work + L.off_rot);
+    int *d_done = reinterpret_cast<int *>(work + L.off_done);
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             jacobi_smem_bytes()));
+        attr_set = true;
+    }
+    std::vector<int> rot((size_t)nmat), done((size_t)nmat, 0);
+    for (int i = 0; i < nmat; ++i) info[i] = -1;
+    const int n_cta = (int)L.cta_mat.size();
+    const int rounds = std::max(1, L.max_nb - 1);
+    const double tol_scale = 4.0e-16;
+    B200_CUDA_CHECK(cudaMemsetAsync(d_done, 0, (size_t)nmat * 4, st));
+    int ndone = 0;
+    for (int sweep = 0; sweep < max_sweeps && ndone < nmat; ++sweep) {
+        B200_CUDA_CHECK(cudaMemsetAsync(d_rot, 0, (size_t)nmat * 4, st));
+        for (int r = 0; r < rounds; ++r) {
+            jacobi_round_kernel<<<n_cta, JTHREADS, jacobi_smem_bytes(), st>>>(wf, d_mats, d_cta, sweep * rounds + r,
+                                                                            d_rot, d_done, tol_scale);
+            B200_CHECK_LAUNCH();
+        }
+        B200_CUDA_CHECK(cudaMemcpyAsync(rot.data(), d_rot, (size_t)nmat * 4, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        bool changed = false;
+        for (int i = 0; i < nmat; ++i) {
+            if (!done[i] && rot[i] == 0) {
+                done[i] = 1;
+                info[i] = sweep + 1;
+                ++ndone;
+                changed = true;
+            }
+        }
+        if (changed && ndone < nmat)
+            B200_CUDA_CHECK(cudaMemcpyAsync(d_done, done.data(), (size_t)nmat * 4, cudaMemcpyHostToDevice, st));
+    }
+    (void)d_cta;
+    return B200_OK;
+}
+
+// sort (descending by norm) on the host; returns permutation pool
+static int sort_norms(const JLayout &L, char *work, cudaStream_t st, bool ascending, std::vector<int> &perm) {
+    const int nmat = (int)L.mats.size();
+    double *wf = reinterpret_cast<double *>(work);
+    JMat *d_mats = reinterpret_cast<JMat *>(work + L.off_mats);
+    dim3 grid((unsigned)std::max(1, L.max_q), (unsigned)nmat);
+    jacobi_norms_kernel<<<grid, 128, 0, st>>>(wf, d_mats);
+    B200_CHECK_LAUNCH();
+    perm.assign((size_t)L.perm_elems + 1, 0);
+    std::vector<double> nrm;
+    for (int i = 0; i < nmat; ++i) {
+        const JMat &mt = L.mats[(size_t)i];
+        nrm.resize((size_t)mt.q);
+        B200_CUDA_CHECK(cudaMemcpyAsync(nrm.data(), wf + mt.snorm_off, (size_t)mt.q * sizeof(double),
+                                        cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        int *pp = perm.data() + mt.perm_off;
+        std::iota(pp, pp + mt.q, 0);
+        if (ascending)
+            std::stable_sort(pp, pp + mt.q, [&](int a, int b) { return nrm[a] < nrm[b]; });
+        else
+            std::stable_sort(pp, pp + mt.q, [&](int a, int b) { return nrm[a] > nrm[b]; });
+    }
+    int *d_perm = reinterpret_cast<int *>(work + L.off_perm);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int64_t b200_block_svd_worksize(int64_t nblocks, const int64_t *m, const int64_t *n) {
+    if (nblocks <= 0) return 256;
+    JLayout L;
+    make_layout(nblocks, m, n, false, L);
+    return L.total_bytes;
+}
+
+extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64_t *n, const int64_t *a_off,
+                                  const int64_t *u_off, const int64_t *s_off, const int64_t *vt_off, const double *A,
+                                  double *U, double *S, double *VT, void *work_dev, int64_t work_bytes,
+                                  int32_t *info, b200_stream_t stream) {
+    if (nblocks <= 0) return B200_OK;
+    if (nblocks > 65535) return set_error(B200_ERR_ARG, "too many blocks for one SVD batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    JLayout L;
+    make_layout(nblocks, m, n, false, L);
+    if (work_bytes < L.total_bytes) return set_error(B200_ERR_ARG, "SVD work buffer too small: %lld < %lld",
+                                                     (long long)work_bytes, (long long)L.total_bytes);
+    for (int64_t i = 0; i < nblocks; ++i) {
+        if (m[i] <= 0 || n[i] <= 0) return set_error(B200_ERR_ARG, "empty block in SVD batch");
+        JMat &mt = L.mats[(size_t)i];
+        mt.a_off = a_off[i];
+        mt.u_off = u_off[i];
+        mt.s_off = s_off[i];
+        mt.vt_off = vt_off[i];
+    }
+    char *work = reinterpret_cast<char *>(work_dev);
+    const int nmat = (int)nblocks;
+    B200_CUDA_CHECK(cudaMemsetAsync(work, 0, (size_t)L.off_mats, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(work + L.off_mats, L.mats.data(), (size_t)nmat * sizeof(JMat),
+                                    cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(work + L.off_cta, L.cta_mat.data(), L.cta_mat.size() * 4, cudaMemcpyHostToDevice, st));
+    JMat *d_mats = reinterpret_cast<JMat *>(work + L.off_mats);
+    double *wf = reinterpret_cast<double *>(work);
+    {
+        int64_t max_elems = 0;
+        for (auto &mt : L.mats) max_elems = std::max<int64_t>(max_elems, (int64_t)mt.q * mt.p);
+        int64_t gx = std::min<int64_t>(std::max<int64_t>(1, (max_elems + 1023) / 1024), 2048);
+        svd_init_kernel<<<dim3((unsigned)gx, (unsigned)nmat), 256, 0, st>>>(wf, d_mats, A);
+        B200_CHECK_LAUNCH();
+    }
+    int rc = run_jacobi(L, work, st, info, 40);
+    if (rc) return rc;
+    std::vector<int> perm;
+    rc = sort_norms(L, work, st, false, perm);
+    if (rc) return rc;
+    svd_finalize_kernel<<<dim3((unsigned)std::max(1, L.max_q), (unsigned)nmat), 128, 0, st>>>(
+        wf, d_mats, reinterpret_cast<int *>(work + L.off_perm), U, S, VT);
+    B200_CHECK_LAUNCH();
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < nmat; ++i)
+        if (info[i] < 0) return set_error(B200_ERR_NOCONV, "block Jacobi SVD did not converge for block %d", i);
+    return B200_OK;
+}
+
+extern "C" int64_t b200_block_eigh_worksize(int64_t nblocks, const int64_t *n) {
+    if (nblocks <= 0) return 256;
+    JLayout L;
+    make_layout(nblocks, n, n, true, L);
+    return L.total_bytes;
+}
+
+extern "C" int b200_block_eigh_f64(int64_t nblocks, const int64_t *n, const int64_t *a_off, const int64_t *w_off,
+                                   const int64_t *v_off, const double *A, double *Wout, double *V, void *work_dev,
+                                   int64_t work_bytes, int32_t *info, b200_stream_t stream) {
+    if (nblocks <= 0) return B200_OK;
+    if (nblocks > 65535) return set_error(B200_ERR_ARG, "too many blocks for one eigh batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    JLayout L;
+    make_layout(nblocks, n, n, true, L);
+    if (work_bytes < L.total_bytes) return set_error(B200_ERR_ARG, "eigh work buffer too small");
+    for (int64_t i = 0; i < nblocks; ++i) {
+        if (n[i] <= 0) return set_error(B200_ERR_ARG, "empty block in eigh batch");
+        JMat &mt = L.mats[(size_t)i];
+        mt.a_off = a_off[i];
+        mt.s_off = w_off[i];
+        mt.vt_off = v_off[i];
+    }
+    char *work = reinterpret_cast<char *>(work_dev);
+    const int nmat = (int)nblocks;
+    B200_CUDA_CHECK(cudaMemsetAsync(work, 0, (size_t)L.off_mats, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(work + L.off_mats, L.mats.data(), (size_t)nmat * sizeof(JMat),
+                                    cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(work + L.off_cta, L.cta_mat.data(), L.cta_mat.size() * 4, cudaMemcpyHostToDevice, st));
+    JMat *d_mats = reinterpret_cast<JMat *>(work + L.off_mats);
+    double *wf = reinterpret_cast<double *>(work);
+    eigh_shift_kernel<<<nmat, 256, 0, st>>>(d_mats, A);
+    B200_CHECK_LAUNCH();
+    {
+        int64_t max_elems = 0;
+        for (auto &mt : L.mats) max_elems = std::max<int64_t>(max_elems, (int64_t)mt.q * mt.p);
+        int64_t gx = std::min<int64_t>(std::max<int64_t>(1, (max_elems + 1023) / 1024), 2048);
+        eigh_init_kernel<<<dim3((unsigned)gx, (unsigned)nmat), 256, 0, st>>>(wf, d_mats, A);
+        B200_CHECK_LAUNCH();
+    }
+    int rc = run_jacobi(L, work, st, info, 40);
+    if (rc) return rc;
+    std::vector<int> perm;
+    rc = sort_norms(L, work, st, true, perm);
+    if (rc) return rc;
+    eigh_finalize_kernel<<<dim3((unsigned)std::max(1, L.max_q), (unsigned)nmat), 128, 0, st>>>(
+        wf, d_mats, reinterpret_cast<int *>(work + L.off_perm), Wout, V);
+    B200_CHECK_LAUNCH();
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < nmat; ++i)
+        if (info[i] < 0) return set_error(B200_ERR_NOCONV, "block Jacobi eigh did not converge for block %d", i);
+    return B200_OK;
+}

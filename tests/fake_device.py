@@ -1,0 +1,148 @@
+"""TEST DOUBLE of the device library -- test infrastructure, never shipped, never imported by the package.
+
+`FakeDeviceLib` has the method surface of :class:`tenpy_b200._lib.DeviceLib` but executes every call
+with numpy on CPU ``torch`` tensors.  It exists so that the HOST logic of tenpy_b200 (charge bookkeeping,
+block layouts, index plans, the DMRG driver) can be unit-tested in the ``-m "not gpu"`` suite on a box
+without a GPU.  It is installed by the ``fake_device`` fixture of ``tests/conftest.py`` through
+``backend.use_library``; the product never selects it by itself, and no GPU test uses it: the parity
+tests proper (``-m gpu``) run the real CUDA kernels and compare against ``oracle/``.
+
+The contraction *plan* (integer bookkeeping) is still built by the real host code of
+``libb200npc.so`` (``b200_tdot_plan_create`` needs no device), so that code is covered here too.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from tenpy_b200 import _lib
+
+
+class _FakePlan:
+    def __init__(self, real):
+        self.real = real
+        self.n_c, self.n_pairs, self.c_size, self.flops = real.n_c, real.n_pairs, real.c_size, real.flops
+        self.c_qdata, self.c_off, self.c_rows, self.c_cols = real.c_qdata, real.c_off, real.c_rows, real.c_cols
+        self._pairs = real.pairs()
+
+    def pairs(self):
+        return self._pairs
+
+    def run(self, A, B, C):
+        a, b, c = A.numpy(), B.numpy(), C.numpy()
+        pair_ptr, a_off, b_off, k = self._pairs
+        for t in range(self.n_c):
+            m, n = int(self.c_rows[t]), int(self.c_cols[t])
+            acc = np.zeros((m, n))
+            for p in range(pair_ptr[t], pair_ptr[t + 1]):
+                kk = int(k[p])
+                acc += a[a_off[p]:a_off[p] + m * kk].reshape(m, kk) @ b[b_off[p]:b_off[p] + kk * n].reshape(kk, n)
+            c[self.c_off[t]:self.c_off[t] + m * n] = acc.reshape(-1)
+
+
+class FakeDeviceLib:
+    name = 'FAKE numpy test double (tests only)'
+
+    def __init__(self):
+        self.torch = torch
+        self.c = _lib.load_library()      # host-only entry points of the real library
+        self.device = torch.device('cpu')
+        self.calls = {}
+
+    def _count(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    def stream(self):
+        return None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.B200Error(self.c.b200_last_error().decode())
+
+    def synchronize(self):
+        pass
+
+    def tdot_plan(self, *args):
+        self._count('tdot_plan')
+        return _FakePlan(_lib.DeviceLib.tdot_plan(self, *args))
+
+    def axpy(self, n, alpha, X, Y):
+        self._count('axpy')
+        Y.numpy()[:n] += alpha * X.numpy()[:n]
+
+    def scal(self, n, alpha, X):
+        self._count('scal')
+        X.numpy()[:n] *= alpha
+
+    def dot(self, n, X, Y, scratch, out):
+        self._count('dot')
+        out.numpy()[0] = float(np.dot(X.numpy()[:n], Y.numpy()[:n]))
+
+    def axpy_segments(self, n_seg, seg_dev, max_len, alpha, X, Y):
+        self._count('axpy_segments')
+        x, y = X.numpy(), Y.numpy()
+        for xo, yo, ln in seg_dev.numpy():
+            y[yo:yo + ln] += alpha * x[xo:xo + ln]
+
+    def dot_segments(self, n_seg, seg_dev, max_len, X, Y, scratch, out):
+        self._count('dot_segments')
+        x, y = X.numpy(), Y.numpy()
+        out.numpy()[0] = sum(float(np.dot(x[xo:xo + ln], y[yo:yo + ln])) for xo, yo, ln in seg_dev.numpy())
+
+    def lanczos_update(self, n, alpha, V1, beta, V0, W, scratch, out):
+        self._count('lanczos_update')
+        w = W.numpy()
+        w[:n] -= alpha * V1.numpy()[:n]
+        if V0 is not None:
+            w[:n] -= beta * V0.numpy()[:n]
+        out.numpy()[0] = float(np.dot(w[:n], w[:n]))
+
+    def copy_blocks(self, task_host, task_dev, SRC, DST):
+        self._count('copy_blocks')
+        src, dst = SRC.numpy(), DST.numpy()
+        for rec in np.asarray(task_host).reshape(-1, _lib.COPY_REC):
+            soff, doff, n, rank = (int(x) for x in rec[:4])
+            shape = rec[4:4 + rank]
+            ss = rec[4 + _lib.COPY_MAXRANK:4 + _lib.COPY_MAXRANK + rank]
+            ds = rec[4 + 2 * _lib.COPY_MAXRANK:4 + 2 * _lib.COPY_MAXRANK + rank]
+            assert n == int(np.prod(shape))
+            idx = np.indices(tuple(int(s) for s in shape)).reshape(rank, -1)
+            so = soff + (idx * ss[:, None]).sum(axis=0)
+            do = doff + (idx * ds[:, None]).sum(axis=0)
+            dst[do] = src[so]
+
+    def take_blocks(self, task_host, task_dev, idx_dev, SRC, DST):
+        self._count('take_blocks')
+        src, dst, pool = SRC.numpy(), DST.numpy(), idx_dev.numpy()
+        for soff, doff, outer, nk, inner, slen, ioff in np.asarray(task_host).reshape(-1, _lib.TAKE_REC):
+            s = src[soff:soff + outer * slen * inner].reshape(outer, slen, inner)
+            dst[doff:doff + outer * nk * inner] = s[:, pool[ioff:ioff + nk], :].reshape(-1)
+
+    def scale_axis(self, task_host, task_dev, S_dev, X):
+        self._count('scale_axis')
+        x, s = X.numpy(), S_dev.numpy()
+        for off, outer, ln, inner, soff in np.asarray(task_host).reshape(-1, _lib.SCALE_REC):
+            v = x[off:off + outer * ln * inner].reshape(outer, ln, inner)
+            v *= s[soff:soff + ln][None, :, None]
+
+    def block_svd(self, m, n, a_off, u_off, s_off, vt_off, A, U, S, VT):
+        self._count('block_svd')
+        a, u, s, vt = A.numpy(), U.numpy(), S.numpy(), VT.numpy()
+        for i in range(len(m)):
+            mi, ni = int(m[i]), int(n[i])
+            k = min(mi, ni)
+            uu, ss, vv = np.linalg.svd(a[a_off[i]:a_off[i] + mi * ni].reshape(mi, ni), full_matrices=False)
+            u[u_off[i]:u_off[i] + mi * k] = uu.reshape(-1)
+            s[s_off[i]:s_off[i] + k] = ss
+            vt[vt_off[i]:vt_off[i] + k * ni] = vv.reshape(-1)
+        return np.ones(len(m), dtype=np.int32)
+
+    def block_eigh(self, n, a_off, w_off, v_off, A, W, V):
+        self._count('block_eigh')
+        a, w, v = A.numpy(), W.numpy(), V.numpy()
+        for i in range(len(n)):
+            ni = int(n[i])
+            ww, vv = np.linalg.eigh(a[a_off[i]:a_off[i] + ni * ni].reshape(ni, ni))
+            w[w_off[i]:w_off[i] + ni] = ww
+            v[v_off[i]:v_off[i] + ni * ni] = vv.reshape(-1)
+        return np.ones(len(n), dtype=np.int32)
