@@ -1,0 +1,210 @@
+"""The two-site effective Hamiltonian and the density-matrix mixer.
+
+Host-side mirror of the reference ``tenpy/algorithms/mps_common.py``: `TwoSiteH` (:1245; `matvec` :1321,
+`combine_Heff` :1350, `combine_theta` :1374, `update_LP` :1421, `update_RP` :1430) and
+`DensityMatrixMixer` (:1903; `mix_rho` :1972, `svd_from_rho` :2029, `_mix_LR` :1846).  The contraction
+sequences are the reference's; each ``npc.tensordot`` is one grouped FP64 tensor-core GEMM launch.
+"""
+# Copyright (C) 2026 tenpy_b200 authors. Apache-2.0.
+
+import numpy as np
+
+from ..linalg import np_conserved as npc
+from ..linalg.truncation import truncate
+
+__all__ = ['TwoSiteH', 'DensityMatrixMixer']
+
+
+class TwoSiteH:
+    r"""Effective Hamiltonian ``LP--W0--W1--RP`` acting on the two-site wave function (reference :1245).
+
+    With ``combine=True`` (default of the DMRG engine) `LHeff` (labels ``'(vR*.p0)', 'wR', '(vR.p0*)'``)
+    and `RHeff` (labels ``'wL', '(p1*.vL)', '(p1.vL*)'``) are formed once per bond and one `matvec` is two
+    contractions: ``LHeff . theta`` and ``(..) . RHeff``, dense cost :math:`4 D d^3 \chi^3` flops."""
+    length = 2
+    acts_on = ['vL', 'p0', 'p1', 'vR']
+
+    def __init__(self, env, i0, combine=False, move_right=True):
+        self.i0 = i0
+        self.LP = env.get_LP(i0)
+        self.RP = env.get_RP(i0 + 1)
+        self.W0 = env.H.get_W(i0).replace_labels(['p', 'p*'], ['p0', 'p0*'])
+        self.W1 = env.H.get_W(i0 + 1).replace_labels(['p', 'p*'], ['p1', 'p1*'])
+        self.dtype = env.H.dtype
+        self.combine = combine
+        self.N = (self.LP.get_leg('vR').ind_len * self.W0.get_leg('p0').ind_len *
+                  self.W1.get_leg('p1').ind_len * self.RP.get_leg('vL').ind_len)
+        if combine:
+            self.combine_Heff(env)
+
+    def matvec(self, theta):
+        """Apply the effective Hamiltonian to `theta` (reference mps_common.py:1321)."""
+        labels = theta.get_leg_labels()
+        if self.combine:
+            theta = npc.tensordot(self.LHeff, theta, axes=['(vR.p0*)', '(vL.p0)'])
+            theta = npc.tensordot(theta, self.RHeff, axes=[['wR', '(p1.vR)'], ['wL', '(p1*.vL)']])
+            theta.ireplace_labels(['(vR*.p0)', '(p1.vL*)'], ['(vL.p0)', '(p1.vR)'])
+        else:
+            theta = npc.tensordot(self.LP, theta, axes=['vR', 'vL'])
+            theta = npc.tensordot(self.W0, theta, axes=[['wL', 'p0*'], ['wR', 'p0']])
+            theta = npc.tensordot(theta, self.W1, axes=[['wR', 'p1'], ['wL', 'p1*']])
+            theta = npc.tensordot(theta, self.RP, axes=[['wR', 'vR'], ['wL', 'vL']])
+            theta.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
+        theta.itranspose(labels)
+        return theta
+
+    def combine_Heff(self, env, left=True, right=True):
+        """Reference mps_common.py:1350."""
+        if left:
+            self.LHeff = env._contract_LHeff(self.i0, 'p0')
+            self.pipeL = self.LHeff.get_leg('(vR*.p0)')
+        if right:
+            self.RHeff = env._contract_RHeff(self.i0 + 1, 'p1')
+            self.pipeR = self.RHeff.get_leg('(p1.vL*)')
+        self.acts_on = ['(vL.p0)', '(p1.vR)']
+
+    def combine_theta(self, theta):
+        """Reference mps_common.py:1374."""
+        if self.combine:
+            theta = theta.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR])
+        return theta.itranspose(self.acts_on)
+
+    def to_matrix(self):
+        """Contract `self` to a 2D Array (small systems only; reference :1396)."""
+        if self.combine:
+            contr = npc.tensordot(self.LHeff, self.RHeff, axes=['wR', 'wL'])
+            contr = contr.combine_legs([['(vR*.p0)', '(p1.vL*)'], ['(vR.p0*)', '(p1*.vL)']], qconj=[+1, -1])
+        else:
+            contr = npc.tensordot(self.LP, self.W0, axes=['wR', 'wL'])
+            contr = npc.tensordot(contr, self.W1, axes=['wR', 'wL'])
+            contr = npc.tensordot(contr, self.RP, axes=['wR', 'wL'])
+            contr = contr.combine_legs([['vR*', 'p0', 'p1', 'vL*'], ['vR', 'p0*', 'p1*', 'vL']], qconj=[+1, -1])
+        return contr
+
+    def update_LP(self, env, i, U=None):
+        """Reference mps_common.py:1421."""
+        if self.combine:
+            assert i == self.i0 + 1
+            LP = npc.tensordot(self.LHeff, U, axes=['(vR.p0*)', '(vL.p)'])
+            LP = npc.tensordot(U.conj(), LP, axes=['(vL*.p*)', '(vR*.p0)'])
+            env.set_LP(i, LP, age=env.get_LP_age(i - 1) + 1)
+        else:
+            env.get_LP(i, store=True)
+
+    def update_RP(self, env, i, VH=None):
+        """Reference mps_common.py:1430."""
+        if self.combine:
+            assert i == self.i0
+            RP = npc.tensordot(VH, self.RHeff, axes=['(p.vR)', '(p1*.vL)'])
+            RP = npc.tensordot(RP, VH.conj(), axes=['(p1.vL*)', '(p*.vR*)'])
+            env.set_RP(i, RP, age=env.get_RP_age(i + 1) + 1)
+        else:
+            env.get_RP(i, store=True)
+
+
+def _mix_LR(H, i0, amplitude):
+    """Diagonal mixing matrices on the MPO bond (reference mps_common.py:1846)."""
+    chi_MPO = H.get_W(i0).get_leg('wR').ind_len
+    IdL, IdR = H.get_IdL(i0 + 1), H.get_IdR(i0)
+    mix_L = np.full((chi_MPO,), amplitude)
+    mix_R = np.full((chi_MPO,), amplitude)
+    one = 1. if not H.explicit_plus_hc else 0.5
+    if IdL is not None:
+        mix_L[IdL] = one
+        mix_R[IdL] = 0.
+    if IdR is not None:
+        mix_L[IdR] = 0.
+        mix_R[IdR] = one
+    return mix_L, mix_R, IdL, IdR, H.explicit_plus_hc
+
+
+class DensityMatrixMixer:
+    """Mixer perturbing the reduced density matrices with the MPO (reference mps_common.py:1903).
+
+    Options `amplitude` (1e-5), `decay` (2.), `disable_after` (15) as the reference's `Mixer` (:1560)."""
+
+    def __init__(self, options, sweep_activated=0):
+        options = dict(options or {})
+        self.amplitude = options.get('amplitude', 1.e-5)
+        self.decay = options.get('decay', 2.)
+        self.disable_after = options.get('disable_after', 15)
+        self.sweep_activated = sweep_activated
+        assert self.amplitude <= 1.
+
+    def update_amplitude(self, sweeps):
+        """Reference mps_common.py:1626."""
+        should_disable = False if self.disable_after is None else \
+            sweeps >= self.sweep_activated + self.disable_after
+        if self.amplitude is not None and self.decay is not None:
+            self.amplitude /= self.decay
+            if self.amplitude <= np.finfo('float').eps:
+                should_disable = True
+        return None if should_disable else self
+
+    def mix_and_decompose_2site(self, engine, theta, i0, mix_left, mix_right, qtotal_LR=[None, None]):
+        rho_L, rho_R = self.mix_rho(engine, theta, i0, mix_left, mix_right)
+        return self.svd_from_rho(engine, rho_L, rho_R, theta, qtotal_LR)
+
+    def mix_rho(self, engine, theta, i0, mix_left, mix_right):
+        """Reference mps_common.py:1972."""
+        mix_L, mix_R, IdL, IdR, explicit_plus_hc = _mix_LR(engine.env.H, i0, self.amplitude)
+        eff_H = engine.eff_H
+        if mix_left:
+            LHeff = eff_H.LHeff if hasattr(eff_H, 'LHeff') else engine.env._contract_LHeff(i0)
+            rho_L = npc.tensordot(LHeff, theta, axes=['(vR.p0*)', '(vL.p0)'])
+            rho_L.ireplace_label('(vR*.p0)', '(vL.p0)')
+            rho_c = rho_L.conj()
+            rho_L = rho_L.scale_axis(mix_L, 'wR')
+            rho_L = npc.tensordot(rho_L, rho_c, axes=[['wR', '(p1.vR)'], ['wR*', '(p1*.vR*)']])
+            if IdL is None:
+                rho_L = rho_L + npc.tensordot(theta, theta.conj(), axes=['(p1.vR)', '(p1*.vR*)'])
+        else:
+            rho_L = npc.tensordot(theta, theta.conj(), axes=['(p1.vR)', '(p1*.vR*)'])
+        if mix_right:
+            RHeff = eff_H.RHeff if hasattr(eff_H, 'RHeff') else engine.env._contract_RHeff(i0 + 1)
+            rho_R = npc.tensordot(theta, RHeff, axes=['(p1.vR)', '(p1*.vL)'])
+            rho_R.ireplace_label('(p1.vL*)', '(p1.vR)')
+            rho_c = rho_R.conj()
+            rho_R = rho_R.scale_axis(mix_R, 'wL')
+            rho_R = npc.tensordot(rho_c, rho_R, axes=[['wL*', '(vL*.p0*)'], ['wL', '(vL.p0)']])
+            if IdR is None:
+                rho_R = rho_R + npc.tensordot(theta.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)'])
+        else:
+            rho_R = npc.tensordot(theta.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)'])
+        return rho_L, rho_R
+
+    def svd_from_rho(self, engine, rho_L, rho_R, theta, qtotal_LR):
+        """Reference mps_common.py:2029."""
+        chinfo = theta.chinfo
+        qtotal_L, qtotal_R = qtotal_LR
+        if qtotal_L is None and qtotal_R is None:
+            qtotal_R = theta.qtotal
+        if qtotal_L is None:
+            qtotal_L = chinfo.make_valid(theta.qtotal - qtotal_R)
+        elif qtotal_R is None:
+            qtotal_R = chinfo.make_valid(theta.qtotal - qtotal_L)
+        qtotal_L, qtotal_R = chinfo.make_valid(qtotal_L), chinfo.make_valid(qtotal_R)
+        rho_L.itranspose(['(vL.p0)', '(vL*.p0*)'])
+        rho_R.itranspose(['(p1.vR)', '(p1*.vR*)'])
+        val_L, U = npc.eigh(rho_L)
+        U.iset_leg_labels(['(vL.p0)', 'vR'])
+        val_L[val_L < 0.] = 0.
+        val_L /= np.sum(val_L)
+        S_a = np.sqrt(val_L)
+        keep_L, _, err_L = truncate(S_a, engine.trunc_params)
+        U.iproject(keep_L, axes='vR')
+        U = U.gauge_total_charge(1, qtotal_L)
+        val_R, Vc = npc.eigh(rho_R)
+        Vc.iset_leg_labels(['(p1.vR)', 'vL'])
+        VH = Vc.itranspose(['vL', '(p1.vR)'])
+        val_R[val_R < 0.] = 0.
+        val_R /= np.sum(val_R)
+        keep_R, _, err_R = truncate(np.sqrt(val_R), engine.trunc_params)
+        VH.iproject(keep_R, axes='vL')
+        VH = VH.gauge_total_charge(0, qtotal_R)
+        theta = npc.tensordot(U.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)'])
+        theta = npc.tensordot(theta, VH.conj(), axes=['(p1.vR)', '(p1*.vR*)'])
+        theta.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
+        theta /= theta.norm()
+        S_a = S_a[keep_L]
+        return U, theta, VH, err_L + err_R, S_a

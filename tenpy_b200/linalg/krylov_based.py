@@ -1,0 +1,176 @@
+"""Lanczos ground state search on device-resident Arrays.
+
+Host-side mirror of the reference ``tenpy/linalg/krylov_based.py`` (class `LanczosGroundState` :584,
+`KrylovBased` :30): same options (`N_min`, `N_max`, `P_tol`, `E_tol`, `min_gap`, `N_cache`, `reortho`,
+`cutoff`, `E_shift`), same three-term recurrence, same convergence test (`_converged` :677) and same
+result assembly (`_calc_result_full` :160).  The control flow and the tridiagonal ``eigh`` (at most
+``(N_max+1)^2`` numbers) stay on the host, as in the reference; every vector operation is a kernel over the
+packed HBM buffers (``matvec`` = 2 grouped GEMMs, `inner` / `norm` = dot kernels, axpy / scal).
+"""
+# Copyright (C) 2026 tenpy_b200 authors. Apache-2.0.
+
+import logging
+
+import numpy as np
+
+from . import np_conserved as npc
+from .. import backend
+
+logger = logging.getLogger(__name__)
+
+__all__ = ['KrylovBased', 'LanczosGroundState', 'lanczos']
+
+
+class KrylovBased:
+    """Base class: option parsing, cache and result assembly (reference krylov_based.py:30)."""
+
+    def __init__(self, H, psi0, options):
+        self.H = H
+        self.psi0 = psi0.copy()
+        self._psi0_norm = None
+        self.options = options = dict(options) if options is not None else {}
+        self.N_min = int(options.get('N_min', 2))
+        self.N_max = int(options.get('N_max', 20))
+        self.N_cache = self.N_max
+        self.P_tol = float(options.get('P_tol', 1.e-14))
+        self.min_gap = float(options.get('min_gap', 1.e-12))
+        self.reortho = bool(options.get('reortho', False))
+        self.E_shift = options.get('E_shift', None)
+        if self.E_shift is not None:
+            raise NotImplementedError('E_shift')
+        if self.N_min < 2:
+            raise ValueError('Should perform at least 2 steps.')
+        self._cutoff = float(options.get('cutoff', np.finfo(np.float64).eps * 100))
+        self._cache = []
+        self.Es = np.zeros([self.N_max, self.N_max], dtype=np.float64)
+        self._h_krylov = np.zeros([self.N_max + 1, self.N_max + 1], dtype=np.float64)
+        self._result_krylov = None
+
+    def _to_cache(self, psi):
+        cache = self._cache
+        cache.append(psi)
+        if len(cache) > self.N_cache:
+            cache.pop(0)
+
+    def _calc_result_full(self, N):
+        """``psi_f = sum_k result_krylov[k] psi[k]`` (reference krylov_based.py:160)."""
+        vf = self._result_krylov
+        assert N == len(vf) > 1
+        psif = self.psi0 * vf[0]
+        len_cache = len(self._cache)
+        for k in range(1, min(len_cache + 1, N)):
+            psif.iadd_prefactor_other(vf[N - k], self._cache[-k])
+        self._cache = []
+        self._rebuild_krylov_for_result_full(psif, N - len_cache - 1)
+        psif_norm = npc.norm(psif)
+        if abs(1. - psif_norm) > 1.e-5:
+            logger.warning('poorly conditioned H matrix in KrylovBased! |psi_0| = %f', psif_norm)
+        psif.iscale_prefactor(1. / psif_norm)
+        return psif
+
+
+class LanczosGroundState(KrylovBased):
+    """Lanczos algorithm for the ground state of a hermitian `H` (reference krylov_based.py:584).
+
+    `H` needs a method ``matvec(Array) -> Array``; `psi0` is the start vector."""
+
+    def __init__(self, H, psi0, options):
+        super().__init__(H, psi0, options)
+        self.E_tol = float(self.options.get('E_tol', np.inf))
+        self.N_cache = int(self.options.get('N_cache', self.N_max))
+        if self.N_cache < 2:
+            raise ValueError('Need to cache at least two vectors.')
+
+    def run(self):
+        """Returns ``(E0, psi0, N)`` (reference krylov_based.py:614)."""
+        N = self._build_krylov()
+        E0 = self.Es[N - 1, 0]
+        if N == 1:
+            return E0, self.psi0.copy(), N
+        return E0, self._calc_result_full(N), N
+
+    def _build_krylov(self):
+        """Reference krylov_based.py:645."""
+        h = self._h_krylov
+        w = self.psi0
+        beta = npc.norm(w)
+        if beta < self._cutoff:
+            raise ValueError('Norm of self.psi0 too small: {0!s}'.format(beta))
+        if self._psi0_norm is None:
+            self._psi0_norm = beta
+        k = 0
+        for k in range(self.N_max):
+            w.iscale_prefactor(1. / beta)
+            self._to_cache(w)
+            w = self.H.matvec(w)
+            alpha = float(npc.inner(w, self._cache[-1], axes='range', do_conj=True))
+            h[k, k] = alpha
+            self._calc_result_krylov(k)
+            fused = (not self.reortho) and w._layout.same_blocks(self._cache[-1]._layout) and \
+                (k == 0 or w._layout.same_blocks(self._cache[-2]._layout))
+            if fused:
+                # w -= alpha v_k + beta v_{k-1};  beta' = |w|   in ONE pass (b200_lanczos_update_f64)
+                lib = backend.get_lib()
+                out = backend.scalar_out()
+                v0 = self._cache[-2]._buf if k > 0 else None
+                lib.lanczos_update(w._layout.size, alpha, self._cache[-1]._buf, beta if k > 0 else 0., v0, w._buf,
+                                   backend.dot_scratch(), out)
+                beta = float(np.sqrt(backend.read_scalar(out)))
+            else:
+                w.iadd_prefactor_other(-alpha, self._cache[-1])
+                if self.reortho:
+                    for c in self._cache[:-1]:
+                        w.iadd_prefactor_other(-npc.inner(c, w, axes='range', do_conj=True), c)
+                elif k > 0:
+                    w.iadd_prefactor_other(-beta, self._cache[-2])
+                beta = npc.norm(w)
+            h[k, k + 1] = h[k + 1, k] = beta
+            if abs(beta) < self._cutoff or (k + 1 >= self.N_min and self._converged(k)):
+                break
+        return k + 1
+
+    def _converged(self, k):
+        """Reference krylov_based.py:677."""
+        v0 = self._result_krylov
+        E = self.Es[k, :]
+        RitzRes = abs(v0[k]) * self._h_krylov[k, k + 1]
+        gap = max(E[1] - E[0], self.min_gap)
+        P_err = (RitzRes / gap)**2
+        Delta_E0 = self.Es[k - 1, 0] - E[0]
+        return P_err < self.P_tol and Delta_E0 < self.E_tol
+
+    def _rebuild_krylov_for_result_full(self, psif, N_max):
+        """Reference krylov_based.py:686 (only needed if N_cache < N)."""
+        vf = self._result_krylov
+        h = self._h_krylov
+        w = self.psi0
+        beta = 0.
+        for k in range(0, N_max):
+            self._to_cache(w)
+            w = self.H.matvec(w)
+            alpha = h[k, k]
+            w.iadd_prefactor_other(-alpha, self._cache[-1])
+            if self.reortho:
+                for c in self._cache[:-1]:
+                    w.iadd_prefactor_other(-npc.inner(c, w, axes='range', do_conj=True), c)
+            elif k > 0:
+                w.iadd_prefactor_other(-beta, self._cache[-2])
+            beta = h[k, k + 1]
+            w.iscale_prefactor(1. / beta)
+            psif.iadd_prefactor_other(vf[k + 1], w)
+
+    def _calc_result_krylov(self, k):
+        """Ground state of the tridiagonal ``h[:k+1, :k+1]`` on the host (reference krylov_based.py:705)."""
+        h = self._h_krylov
+        if k == 0:
+            self.Es[0, 0] = h[0, 0]
+            self._result_krylov = np.ones(1, np.float64)
+        else:
+            E_kr, v_kr = np.linalg.eigh(h[:k + 1, :k + 1])
+            self.Es[k, :k + 1] = E_kr
+            self._result_krylov = v_kr[:, 0]
+
+
+def lanczos(H, psi, options={}):
+    """Function wrapper (reference krylov_based.py `lanczos`)."""
+    return LanczosGroundState(H, psi, options).run()

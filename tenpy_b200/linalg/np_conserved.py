@@ -762,8 +762,9 @@ class Array:
             new_qconj = old.qconj
         newqtotal = self.chinfo.make_valid(newqtotal)
         chdiff = newqtotal - self.qtotal
-        new_charges = (old.charges * old.qconj + chdiff) * new_qconj if new_qconj == old.qconj else \
-            -(old.charges * old.qconj + chdiff)
+        new_charges = old.charges + old.qconj * chdiff
+        if new_qconj != old.qconj:
+            new_charges = -new_charges
         leg = LegCharge.from_qind(self.chinfo, old.slices, self.chinfo.make_valid(new_charges), new_qconj)
         res.legs[ax] = leg
         res.qtotal = newqtotal
