@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- DMRG sweep wall-clock and effective-H matvec throughput, 1..N B200 vs the reference CPU path.
+
+Workload (BASELINE.json configs[1]): TFIChain L=100, two-site DMRG at chi=1024, no charge conservation
+(dense-block path).  One *step* = one full DMRG sweep = 2(L-2) = 196 two-site bond updates through
+``tenpy_b200.algorithms.dmrg.TwoSiteDMRGEngine.sweep`` (Lanczos with the effective-H matvec, block SVD +
+truncation, environment update), starting from a synthetic random right-canonical-on-average MPS whose inner
+bonds are saturated at chi.  As in the reference's own benchmark harness
+(tests/benchmark/dmrg_infinite.py:31-37) the Lanczos iteration count is fixed (N_min = N_max = 10) and
+``svd_min`` is tiny so that chi stays saturated -> every step does identical work.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # CPU: oracle restatement of the reference path
+
+N > 1 (launched by torchrun): the path shards over independent DMRG runs (a field scan, BASELINE.json
+configs[4]); rank r runs the same workload at g = 1 + 0.02 r, the only collectives are an NCCL broadcast of
+the model template and an all-gather of the per-run results; ``value`` = max-over-ranks sweep time / N
+(seconds per sweep of the whole job, weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'dmrg_two_site_sweep_wall_clock'
+UNIT = 's'
+FP64_TENSOR_PEAK_TFLOPS = 37.0   # B200 (HGX) FP64 tensor/DFMA spec; MEASURED_PEAKS.json has no FP64 entry
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=1)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--L', type=int, default=100)
+    ap.add_argument('--chi', type=int, default=1024)
+    ap.add_argument('--lanczos-N', type=int, default=10)
+    ap.add_argument('--cpu-bonds', type=int, default=2, help='bond updates per CPU sample')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+# ------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(',')]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.5)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]),
+                'power_w_max': max(float(s[2]) for s in self.samples), 'reasons': sorted(reasons),
+                'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU (oracle) arm
+def cpu_bond_sample(chi, d, D, lanczos_N, n_bonds, seed=0):
+    """time `n_bonds` two-site updates at the chain centre (full chi) with the dense CPU oracle."""
+    from oracle import dmrg_dense as od
+    rng = np.random.default_rng(seed)
+    n = chi * d
+    LHeff = rng.standard_normal((n, D, n))
+    LHeff = LHeff + LHeff.transpose(2, 1, 0)
+    RHeff = rng.standard_normal((D, n, n))
+    RHeff = RHeff + RHeff.transpose(0, 2, 1)
+    theta = rng.standard_normal((n, n))
+    theta /= np.linalg.norm(theta)
+    trunc = dict(chi_max=chi, svd_min=1e-45, trunc_cut=None)
+    lan = dict(N_min=lanczos_N, N_max=lanczos_N)
+    t0 = time.perf_counter()
+    tm = 0.
+    for b in range(n_bonds):
+        t1 = time.perf_counter()
+        od.matvec(LHeff, RHeff, theta)
+        tm += time.perf_counter() - t1
+        E0, U, S, VH, env, N = od.bond_update(LHeff, RHeff, theta, trunc, lan, move_right=(b % 2 == 0))
+    dt = time.perf_counter() - t0 - tm
+    return dt / n_bonds, tm / n_bonds
+
+
+def cpu_sweep_estimate(args, n_bonds):
+    """CPU sweep estimate = (number of full-chi bond updates per sweep) x (time of one such update)."""
+    d, D = 2, 3
+    full = n_full_bonds(args.L, args.chi, d)
+    per_bond, t_matvec = cpu_bond_sample(args.chi, d, D, args.lanczos_N, n_bonds)
+    from oracle import dmrg_dense as od
+    fl = od.matvec_flops(args.chi * d, D, args.chi * d)
+    return {'sweep_s': full * per_bond, 'per_bond_s': per_bond, 'matvec_s': t_matvec,
+            'matvec_gflops': fl / t_matvec / 1e9, 'full_chi_bonds': full}
+
+
+def n_full_bonds(L, chi, d):
+    """number of the 2(L-2) bond updates of a sweep whose theta has the full (chi d) x (d chi) size"""
+    dims = [min(d**i, d**(L - i), chi) for i in range(L + 1)]
+    i0s = list(range(0, L - 2)) + list(range(L - 2, 0, -1))
+    return sum(1 for i0 in i0s if dims[i0] == chi and dims[i0 + 2] == chi)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    vals = []
+    for it in range(args.warmup + args.steps):
+        est = cpu_sweep_estimate(args, 1)
+        if it >= args.warmup:
+            vals.append(est)
+    v = float(np.mean([e['sweep_s'] for e in vals]))
+    sample = ('1 bond update at full chi per step (oracle/dmrg_dense.py: %d Lanczos matvecs + gesdd + env update), '
+              'x %d full-chi bonds of the sweep' % (args.lanczos_N, vals[0]['full_chi_bonds']))
+    line = {'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': v * 1e3, 'higher_is_better': False, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
+            'config': workload_config(args, 1),
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                             'matvec_gflops': float(np.mean([e['matvec_gflops'] for e in vals]))},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {'workload': 'TFIChain L=%d two-site DMRG sweep (%d bond updates) at chi=%d, conserve=None (dense-block '
+                        'path), d=2, MPO D=3, Lanczos N_min=N_max=%d, svd_min=1e-45' %
+                        (args.L, 2 * (args.L - 2), args.chi, args.lanczos_N),
+            'L': args.L, 'chi': args.chi, 'lanczos_N': args.lanczos_N,
+            'parallelism': 'independent DMRG runs (field scan g=1+0.02*rank), %d rank(s)' % n,
+            'l2': 'working set per step (100 x (LP, RP, B) ~ 7 GB) >> 126 MB L2; no explicit flush'}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def synthetic_mps(model, L, chi, d, seed):
+    """random MPS with saturated inner bonds; B ~ N(0, 1/(d chi_r)) is right-isometric on average."""
+    import torch
+    from tenpy_b200 import backend
+    from tenpy_b200.linalg import np_conserved as npc
+    from tenpy_b200.linalg.charges import LegCharge
+    from tenpy_b200.networks.mps import MPS
+    dev = backend.get_lib().device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + seed)
+    dims = [min(d**i, d**(L - i), chi) for i in range(L + 1)]
+    chinfo = model.lat_sites[0].leg.chinfo
+    Bs, Ss = [], []
+    for i in range(L):
+        cl, cr = dims[i], dims[i + 1]
+        n = cl * d * cr
+        n_pad = (n + 15) // 16 * 16
+        buf = torch.zeros(n_pad, dtype=torch.float64, device=dev)
+        buf[:n] = torch.randn(n, dtype=torch.float64, device=dev, generator=gen) / np.sqrt(d * cr)
+        legs = [LegCharge.from_trivial(cl, chinfo, +1), model.lat_sites[i].leg, LegCharge.from_trivial(cr, chinfo, -1)]
+        Bs.append(npc.Array.from_device_buffer(legs, np.zeros((1, 3), np.int64), buf, labels=['vL', 'p', 'vR']))
+        Ss.append(np.ones(cl) / np.sqrt(cl))
+    Ss.append(np.ones(1))
+    return MPS(model.lat_sites, Bs, Ss, 'finite', 'B')
+
+
+def psi_to_host(psi):
+    """D2H of all MPS tensors (the result of a sweep)"""
+    from tenpy_b200 import backend
+    out, nbytes = [], 0
+    for B in psi._B:
+        h = backend.to_host(B._buf)
+        nbytes += h.nbytes
+        out.append(h)
+    return out, nbytes
+
+
+def psi_from_host(psi, host_bufs):
+    """H2D of all MPS tensors from pinned host memory"""
+    nbytes = 0
+    for B, h in zip(psi._B, host_bufs):
+        B._buf.copy_(h, non_blocking=True)
+        nbytes += h.numel() * 8
+    return nbytes
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from tenpy_b200 import backend
+    from tenpy_b200._lib import DeviceLib
+    lib = backend.use_library(DeviceLib())
+    from tenpy_b200.models import TFIChain
+    from tenpy_b200.algorithms import dmrg
+    d, D = 2, 3
+    L, chi = args.L, args.chi
+
+    # model: rank 0 owns the template (J, g0); NCCL broadcast, every rank patches its own field g
+    tmpl = torch.tensor([1.0, 1.0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.broadcast(tmpl, src=0)
+    J, g0 = float(tmpl[0]), float(tmpl[1])
+    g = g0 + 0.02 * rank
+    model = TFIChain({'L': L, 'J': J, 'g': g, 'conserve': None})
+    psi = synthetic_mps(model, L, chi, d, seed=rank)
+    opts = {'mixer': None, 'combine': True, 'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None},
+            'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N}}
+    eng = dmrg.TwoSiteDMRGEngine(psi, model, opts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up sweeps (the last one with per-family CUDA-event profiling)
+    for w in range(args.warmup):
+        if w == args.warmup - 1:
+            lib.profile = {}
+        eng.sweep()
+    prof = lib.profile_summary() if lib.profile is not None else {}
+    lib.profile = None
+
+    # ---- timed region: exactly K sweeps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    lib.kernel_launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        eng.sweep()
+    ev1.record()
+    barrier()
+    launches = lib.kernel_launch_count()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.summary() if rank == 0 else None
+    E_final = eng.update_stats['E_total'][-1]
+    S_mid = eng._entropy_approx[L // 2]
+    N_lan = float(np.mean(eng.update_stats['N_lanczos'][-2 * (L - 2):]))
+
+    # ---- end-to-end: the same sweep through the public API with HOST buffers (H2D + D2H inside the timer)
+    e2e = None
+    if not args.no_e2e:
+        host, _ = psi_to_host(psi)
+        pinned = [torch.from_numpy(h).pin_memory() for h in host]
+        barrier()
+        t0 = time.perf_counter()
+        h2d = psi_from_host(psi, pinned)
+        eng.env.clear()
+        eng.sweep()
+        _, d2h = psi_to_host(psi)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        e2e = {'value': e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'note': 'MPS tensors from pinned host memory -> sweep (environments rebuilt) -> MPS back to host'}
+
+    # ---- kernel roofline probes at the centre-bond shapes (CUDA events on the launching stream)
+    roof = kernel_probes(lib, chi, d, D)
+
+    # ---- gather over ranks
+    stats = torch.tensor([ms, E_final, S_mid, e2e['value'] if e2e else 0.], dtype=torch.float64, device='cuda')
+    if world > 1:
+        allst = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+        allst = torch.stack(allst).cpu().numpy()
+    else:
+        allst = stats.cpu().numpy()[None, :]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_max = float(allst[:, 0].max())
+    value = ms_max / 1e3 / world
+    peaks, peaks_kind = measured_peaks()
+    total_ms = sum(v[1] for v in prof.values()) or 1.
+    shares = {k: round(v[1] / total_ms, 4) for k, v in prof.items()}
+    dominant = max(shares, key=shares.get) if shares else 'gemm'
+    roofline = roof['svd'] if dominant == 'svd' else roof['gemm']
+    roofline = dict(roofline)
+    roofline['kernel'] = 'jacobi_round_kernel (block SVD)' if dominant == 'svd' else 'grouped_gemm_kernel<128,128> (matvec)'
+    roofline['share_of_step'] = shares.get(dominant)
+    if e2e:
+        e2e['value'] = float(allst[:, 3].max()) / world
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_max, 'higher_is_better': False, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'impl': 'b200',
+            'config': workload_config(args, world), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'roofline': roofline, 'roofline_gemm': roof['gemm'], 'roofline_svd': roof['svd'],
+            'kernel_time_shares': shares, 'kernel_family_ms_per_sweep': {k: round(v[1], 2) for k, v in prof.items()},
+            'matvec_gflops': roof['gemm']['achieved'] * 1e3, 'peaks': peaks_kind,
+            'result': {'E': [float(x) for x in allst[:, 1]], 'S_mid': [float(x) for x in allst[:, 2]],
+                       'N_lanczos_mean': N_lan}}
+    if not args.no_cpu:
+        est = cpu_sweep_estimate(args, args.cpu_bonds)
+        line['cpu_baseline'] = {'value': est['sweep_s'], 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': '%d centre-bond updates (oracle/dmrg_dense.py, numpy/OpenBLAS/LAPACK gesdd) '
+                                          'x %d full-chi bonds per sweep' % (args.cpu_bonds, est['full_chi_bonds']),
+                                'per_bond_s': est['per_bond_s'], 'matvec_gflops': est['matvec_gflops']}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_probes(lib, chi, d, D):
+    """time the two dominant kernels alone on centre-bond shapes (after warm-up, CUDA events)"""
+    import torch
+    from tenpy_b200 import backend
+    from tenpy_b200.linalg import np_conserved as npc
+    peaks, kind = measured_peaks()
+    n = chi * d
+    dev = lib.device
+
+    def rnd(legs):
+        t = torch.randn(int(np.prod([l.ind_len for l in legs])), dtype=torch.float64, device=dev)
+        return npc.Array.from_device_buffer(legs, np.zeros((1, len(legs)), np.int64), t)
+    ci = npc.ChargeInfo()
+    lL, lR, lW = (npc.LegCharge.from_trivial(n, ci, +1), npc.LegCharge.from_trivial(n, ci, -1),
+                  npc.LegCharge.from_trivial(D, ci, -1))
+    LHeff, theta, RHeff = rnd([lL, lW, lL.conj()]), rnd([lL, lR]), rnd([lW.conj(), lR.conj(), lR])
+    reps = 5
+    for _ in range(3):
+        t1 = npc.tensordot(LHeff, theta, axes=[2, 0])
+        t2 = npc.tensordot(t1, RHeff, axes=[[1, 2], [0, 1]])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+        t1 = npc.tensordot(LHeff, theta, axes=[2, 0])
+        t2 = npc.tensordot(t1, RHeff, axes=[[1, 2], [0, 1]])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    flops = 4. * D * d**3 * chi**3
+    tf = flops / (ms * 1e-3) / 1e12
+    gemm = {'bound': 'tensor', 'achieved': tf, 'peak': FP64_TENSOR_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+            'frac': tf / FP64_TENSOR_PEAK_TFLOPS, 'traffic': None, 'ms_per_matvec': ms,
+            'peak_note': 'FP64 DMMA pipe, nominal B200 spec (MEASURED_PEAKS.json has only bf16: %.0f TFLOP/s %s)' %
+                         (peaks.get('bf16_tflops', 0.), kind),
+            'algorithmic': '4 D d^3 chi^3 = %.3e flop per matvec (two grouped GEMM launches)' % flops}
+    # SVD of the centre theta: bytes = 8 (mn + mk + k + kn)
+    from tenpy_b200.linalg.np_conserved import svd
+    svd(theta)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(2):
+        svd(theta)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_svd = ev0.elapsed_time(ev1) / 2
+    by = 8. * (n * n + n * n + n + n * n)
+    gbs = by / (ms_svd * 1e-3) / 1e9
+    svdr = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'],
+            'traffic': None, 'ms_per_svd': ms_svd,
+            'algorithmic': '8 (mn + mk + k + kn) = %.3e bytes per %dx%d block (read A once, write U, S, VH once); '
+                           'the Jacobi iteration itself is compute/latency bound for a block this large' % (by, n, n),
+            'peak_note': 'hbm_gbs %s' % kind}
+    return {'gemm': gemm, 'svd': svdr}
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -46,6 +46,8 @@ const char *b200_last_error(void);
 int b200_device_count(void);
 /* properties of device `dev`: SM count, compute capability, total memory */
 int b200_device_info(int dev, int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes);
+/* number of kernels this library has launched since load (or since the last call with reset != 0) */
+int64_t b200_kernel_launch_count(int reset);
 /* self test of the FP64 tensor-core fragment layouts used by the kernels; out_host[0..3] receive the max
  * abs error of (m16n8k8 path, m8n8k4 path, grouped gemm 128-tile, grouped gemm 64-tile) on a fixed problem */
 int b200_selftest(double *out_host);

@@ -34,6 +34,7 @@ _SIGNATURES = {
     'b200_device_count': (ctypes.c_int, []),
     'b200_device_info': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                         ctypes.POINTER(ctypes.c_int), c_i64p]),
+    'b200_kernel_launch_count': (c_i64, [ctypes.c_int]),
     'b200_selftest': (ctypes.c_int, [c_f64p]),
     'b200_find_row_differences': (ctypes.c_int, [c_i64p, c_i64, c_i64, c_i64p, c_i64p]),
     'b200_lexsort_rows': (ctypes.c_int, [c_i64p, c_i64, c_i64, c_i64p]),
@@ -110,6 +111,27 @@ def _ptr(t):
     return c_vp(t.data_ptr())
 
 
+class _Prof:
+    """records a CUDA-event pair around a library call when ``lib.profile`` is a dict (bench / profiling)."""
+    __slots__ = ('lib', 'cat', 'ev0')
+
+    def __init__(self, lib, cat):
+        self.lib, self.cat, self.ev0 = lib, cat, None
+
+    def __enter__(self):
+        if self.lib.profile is not None:
+            self.ev0 = self.lib.torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev0 is not None:
+            ev1 = self.lib.torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.lib.profile.setdefault(self.cat, []).append((self.ev0, ev1))
+        return False
+
+
 class TdotPlan:
     """Handle of a contraction plan (``b200_tdot_plan``); see include/b200npc.h."""
 
@@ -146,7 +168,8 @@ class TdotPlan:
 
     def run(self, A, B, C):
         lib = self._lib
-        lib._check(lib.c.b200_tdot_plan_run(self._h, _ptr(A), _ptr(B), _ptr(C), lib.stream()))
+        with _Prof(lib, 'gemm'):
+            lib._check(lib.c.b200_tdot_plan_run(self._h, _ptr(A), _ptr(B), _ptr(C), lib.stream()))
 
     def __del__(self):
         try:
@@ -171,6 +194,15 @@ class DeviceLib:
         if not torch.cuda.is_available() or self.c.b200_device_count() < 1:
             raise B200Error('no CUDA device visible: tenpy_b200 computes on a B200 only (no CPU fallback)')
         self.device = torch.device('cuda', torch.cuda.current_device())
+        self.profile = None   # set to {} to collect CUDA-event timings per kernel family
+
+    def profile_summary(self):
+        """{family: (n_calls, total_ms)} of the collected event pairs; synchronises."""
+        self.synchronize()
+        out = {}
+        for cat, evs in (self.profile or {}).items():
+            out[cat] = (len(evs), float(sum(a.elapsed_time(b) for a, b in evs)))
+        return out
 
     # -- plumbing
     def stream(self):
@@ -205,41 +237,50 @@ class DeviceLib:
 
     # -- BLAS-1
     def axpy(self, n, alpha, X, Y):
-        self._check(self.c.b200_axpy_f64(n, float(alpha), _ptr(X), _ptr(Y), self.stream()))
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_axpy_f64(n, float(alpha), _ptr(X), _ptr(Y), self.stream()))
 
     def scal(self, n, alpha, X):
-        self._check(self.c.b200_scal_f64(n, float(alpha), _ptr(X), self.stream()))
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_scal_f64(n, float(alpha), _ptr(X), self.stream()))
 
     def dot(self, n, X, Y, scratch, out):
-        self._check(self.c.b200_dot_f64(n, _ptr(X), _ptr(Y), _ptr(scratch), _ptr(out), self.stream()))
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_dot_f64(n, _ptr(X), _ptr(Y), _ptr(scratch), _ptr(out), self.stream()))
 
     def axpy_segments(self, n_seg, seg_dev, max_len, alpha, X, Y):
-        self._check(self.c.b200_axpy_segments_f64(n_seg, _ptr(seg_dev), max_len, float(alpha), _ptr(X), _ptr(Y),
-                                                  self.stream()))
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_axpy_segments_f64(n_seg, _ptr(seg_dev), max_len, float(alpha), _ptr(X), _ptr(Y),
+                                                      self.stream()))
 
     def dot_segments(self, n_seg, seg_dev, max_len, X, Y, scratch, out):
-        self._check(self.c.b200_dot_segments_f64(n_seg, _ptr(seg_dev), max_len, _ptr(X), _ptr(Y), _ptr(scratch),
-                                                 _ptr(out), self.stream()))
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_dot_segments_f64(n_seg, _ptr(seg_dev), max_len, _ptr(X), _ptr(Y), _ptr(scratch),
+                                                     _ptr(out), self.stream()))
 
     def lanczos_update(self, n, alpha, V1, beta, V0, W, scratch, out):
-        self._check(self.c.b200_lanczos_update_f64(n, float(alpha), _ptr(V1), float(beta), _ptr(V0), _ptr(W),
-                                                   _ptr(scratch), _ptr(out), self.stream()))
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_lanczos_update_f64(n, float(alpha), _ptr(V1), float(beta), _ptr(V0), _ptr(W),
+                                                       _ptr(scratch), _ptr(out), self.stream()))
 
     # -- data movement
     def copy_blocks(self, task_host, task_dev, SRC, DST):
         th, thp = _i64(task_host)
-        self._check(self.c.b200_copy_blocks_f64(th.shape[0], _ptr(task_dev), thp, _ptr(SRC), _ptr(DST),
-                                                self.stream()))
+        with _Prof(self, 'move'):
+            self._check(self.c.b200_copy_blocks_f64(th.shape[0], _ptr(task_dev), thp, _ptr(SRC), _ptr(DST),
+                                                    self.stream()))
 
     def take_blocks(self, task_host, task_dev, idx_dev, SRC, DST):
         th, thp = _i64(task_host)
-        self._check(self.c.b200_take_blocks_f64(th.shape[0], _ptr(task_dev), thp, _ptr(idx_dev), _ptr(SRC),
-                                                _ptr(DST), self.stream()))
+        with _Prof(self, 'move'):
+            self._check(self.c.b200_take_blocks_f64(th.shape[0], _ptr(task_dev), thp, _ptr(idx_dev), _ptr(SRC),
+                                                    _ptr(DST), self.stream()))
 
     def scale_axis(self, task_host, task_dev, S_dev, X):
         th, thp = _i64(task_host)
-        self._check(self.c.b200_scale_axis_f64(th.shape[0], _ptr(task_dev), thp, _ptr(S_dev), _ptr(X),
-                                               self.stream()))
+        with _Prof(self, 'move'):
+            self._check(self.c.b200_scale_axis_f64(th.shape[0], _ptr(task_dev), thp, _ptr(S_dev), _ptr(X),
+                                                   self.stream()))
 
     # -- decompositions
     def block_svd(self, m, n, a_off, u_off, s_off, vt_off, A, U, S, VT):
@@ -248,9 +289,10 @@ class DeviceLib:
         wbytes = int(self.c.b200_block_svd_worksize(nb, ms[1], ns[1]))
         work = self.torch.empty(wbytes, dtype=self.torch.uint8, device=self.device)
         info = np.zeros(nb, dtype=np.int32)
-        self._check(self.c.b200_block_svd_f64(nb, ms[1], ns[1], ao[1], uo[1], so[1], vo[1], _ptr(A), _ptr(U),
-                                              _ptr(S), _ptr(VT), _ptr(work), wbytes, info.ctypes.data_as(c_i32p),
-                                              self.stream()))
+        with _Prof(self, 'svd'):
+            self._check(self.c.b200_block_svd_f64(nb, ms[1], ns[1], ao[1], uo[1], so[1], vo[1], _ptr(A), _ptr(U),
+                                                  _ptr(S), _ptr(VT), _ptr(work), wbytes, info.ctypes.data_as(c_i32p),
+                                                  self.stream()))
         return info
 
     def block_eigh(self, n, a_off, w_off, v_off, A, W, V):
@@ -259,9 +301,13 @@ class DeviceLib:
         wbytes = int(self.c.b200_block_eigh_worksize(nb, ns[1]))
         work = self.torch.empty(wbytes, dtype=self.torch.uint8, device=self.device)
         info = np.zeros(nb, dtype=np.int32)
-        self._check(self.c.b200_block_eigh_f64(nb, ns[1], ao[1], wo[1], vo[1], _ptr(A), _ptr(W), _ptr(V),
-                                               _ptr(work), wbytes, info.ctypes.data_as(c_i32p), self.stream()))
+        with _Prof(self, 'eigh'):
+            self._check(self.c.b200_block_eigh_f64(nb, ns[1], ao[1], wo[1], vo[1], _ptr(A), _ptr(W), _ptr(V),
+                                                   _ptr(work), wbytes, info.ctypes.data_as(c_i32p), self.stream()))
         return info
+
+    def kernel_launch_count(self, reset=False):
+        return int(self.c.b200_kernel_launch_count(1 if reset else 0))
 
     def selftest(self):
         out = np.zeros(4, dtype=np.float64)

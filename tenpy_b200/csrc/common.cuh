@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/b200npc.h"
@@ -23,6 +24,7 @@ int set_error(int code, const char *fmt, ...);
 
 #define B200_CHECK_LAUNCH()                                                                          \
     do {                                                                                             \
+        b200::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                             \
         cudaError_t _e = cudaGetLastError();                                                         \
         if (_e != cudaSuccess)                                                                       \
             return b200::set_error(B200_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__,       \
@@ -30,6 +32,7 @@ int set_error(int code, const char *fmt, ...);
     } while (0)
 
 int sm_count();  // SM count of the current device (cached)
+extern std::atomic<long long> g_kernel_launches;  // every kernel launch of this library is counted
 
 // ---- FP64 tensor-core MMA (DMMA) -----------------------------------------------------------------
 // D(16x8) += A(16x8) * B(8x8), all f64.  Fragment ownership (lane = 4*g + t, g = 0..7, t = 0..3):

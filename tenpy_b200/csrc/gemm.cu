@@ -17,6 +17,7 @@
 namespace b200 {
 
 thread_local std::string g_last_error;
+std::atomic<long long> g_kernel_launches{0};
 
 int set_error(int code, const char *fmt, ...) {
     char buf[1024];
@@ -584,6 +585,10 @@ extern "C" int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m, const in
 }
 
 // ---- misc ABI ------------------------------------------------------------------------------------
+extern "C" int64_t b200_kernel_launch_count(int reset) {
+    long long v = reset ? g_kernel_launches.exchange(0) : g_kernel_launches.load();
+    return (int64_t)v;
+}
 extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
 extern "C" const char *b200_last_error(void) { return g_last_error.c_str(); }
 extern "C" int b200_device_count(void) {

@@ -220,6 +220,17 @@ class Array:
         return res
 
     @classmethod
+    def from_device_buffer(cls, legcharges, qdata, buf, qtotal=None, labels=None):
+        """Wrap an existing packed device buffer (`qdata` must be lex-sorted; `buf` laid out as BlockLayout)."""
+        res = cls(legcharges, np.float64, qtotal, labels)
+        layout, perm = BlockLayout.from_legs(res.legs, qdata)
+        if np.any(perm != np.arange(len(perm))):
+            raise ValueError('qdata has to be lex-sorted')
+        if buf.numel() != layout.size:
+            raise ValueError('buffer has {0} elements, layout needs {1}'.format(buf.numel(), layout.size))
+        return res._set_blocks(layout, buf)
+
+    @classmethod
     def from_ndarray_trivial(cls, data_flat, dtype=None, labels=None):
         """Array without charges from a dense ndarray (reference npc:420)."""
         data_flat = np.asarray(data_flat, dtype=np.float64)
