@@ -32,10 +32,11 @@ constexpr int JLDP = JKC + 4;   // smem row stride of a panel chunk
 constexpr int JTHREADS = 256;
 constexpr int JLDG = JP + 1;
 constexpr int JLDQT = JP + 4;
-constexpr int J_INNER_SWEEPS = 12;
+constexpr int J_INNER_SWEEPS = 4;   // the pivot block only has to be diagonalised "well enough" per round
 
 struct JMat {
     int64_t y_off, w_off, snorm_off;       // element offsets into the f64 work area
+    int64_t prep_off;                      // m + n doubles: squared row / column norms of A (orientation, pre-sort)
     int64_t a_off, u_off, s_off, vt_off;   // element offsets into the caller's buffers
     int32_t m, n;                          // original shape
     int32_t q, p;                          // vectors, vector length
@@ -242,9 +243,11 @@ __global__ void __launch_bounds__(JTHREADS)
                 double c = 1.0, s = 0.0;
                 double lim = tol_in * sqrt(fabs(gpp * gqq));
                 if (fabs(gpq) > lim && fabs(gpq) > 0.0) {
-                    double tau = (gqq - gpp) / (2.0 * gpq);
-                    double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                    c = 1.0 / sqrt(1.0 + tt * tt);
+                    // t = tan(theta) of the Jacobi rotation: one sqrt, one division, one rsqrt
+                    const double aa = gqq - gpp, bb = 2.0 * gpq;
+                    const double hh = sqrt(aa * aa + bb * bb);
+                    const double tt = (aa >= 0.0) ? bb / (aa + hh) : bb / (aa - hh);
+                    c = rsqrt(1.0 + tt * tt);
                     s = tt * c;
                     any = 1;
                 }
@@ -316,22 +319,50 @@ __global__ void __launch_bounds__(JTHREADS)
 }
 
 // ---- init / finalize kernels ---------------------------------------------------------------------
-// SVD init: Y = A or A^T (zero padded), W = identity.  grid (chunks, nmat)
-__global__ void __launch_bounds__(256) svd_init_kernel(double *__restrict__ work, const JMat *__restrict__ mats,
+// squared row norms (first m entries) and column norms (next n entries) of every A: grid (m + n, nmat)
+__global__ void __launch_bounds__(128) svd_prep_kernel(double *__restrict__ work, const JMat *__restrict__ mats,
                                                        const double *__restrict__ A) {
+    __shared__ double red[32];
+    const JMat mt = mats[blockIdx.y];
+    const int v = blockIdx.x;
+    if (v >= mt.m + mt.n) return;
+    const double *a = A + mt.a_off;
+    double s = 0.0;
+    if (v < mt.m) {
+        for (int c = threadIdx.x; c < mt.n; c += blockDim.x) {
+            double x = a[(int64_t)v * mt.n + c];
+            s = fma(x, x, s);
+        }
+    } else {
+        const int c = v - mt.m;
+        for (int r = threadIdx.x; r < mt.m; r += blockDim.x) {
+            double x = a[(int64_t)r * mt.n + c];
+            s = fma(x, x, s);
+        }
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) work[mt.prep_off + v] = s;
+}
+
+// SVD init: Y[r] = vector perm[r] of A (rows of A, or columns if transposed), zero padded; W = permutation.
+// grid (chunks, nmat)
+__global__ void __launch_bounds__(256) svd_init_kernel(double *__restrict__ work, const JMat *__restrict__ mats,
+                                                       const int *__restrict__ perm, const double *__restrict__ A) {
     const JMat mt = mats[blockIdx.y];
     double *Y = work + mt.y_off;
     double *W = work + mt.w_off;
     const double *a = A + mt.a_off;
+    const int *pm = perm + mt.perm_off;
     const int64_t ny = (int64_t)mt.q * mt.p;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ny; e += stride) {
         int r = (int)(e / mt.p), c = (int)(e % mt.p);
-        double v = mt.transposed ? a[(int64_t)c * mt.n + r] : a[(int64_t)r * mt.n + c];
+        int src = pm[r];
+        double v = mt.transposed ? a[(int64_t)c * mt.n + src] : a[(int64_t)src * mt.n + c];
         Y[(int64_t)r * mt.ldy + c] = v;
     }
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < mt.qp; e += stride)
-        W[e * mt.ldw + e] = 1.0;
+        W[e * mt.ldw + (e < mt.q ? pm[e] : e)] = 1.0;
 }
 
 // eigh init: Y = A + shift*I.  shift[mat] was computed by eigh_shift_kernel.
@@ -457,6 +488,8 @@ static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, boo
         off += (int64_t)mt.qp * mt.ldw;
         mt.snorm_off = off;
         off += rup(mt.qp, 16);
+        mt.prep_off = off;
+        off += rup((int64_t)mt.m + mt.n, 16);
         mt.cta_begin = cta;
         for (int c = 0; c < nb / 2; ++c) L.cta_mat.push_back((int)i);
         cta += nb / 2;
@@ -510,6 +543,12 @@ static int run_jacobi(const JLayout &L, char *work, cudaStream_t st, int32_t *in
         }
         B200_CUDA_CHECK(cudaMemcpyAsync(rot.data(), d_rot, (size_t)nmat * 4, cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (getenv("B200_JACOBI_DEBUG")) {
+            long tot = 0;
+            for (int i = 0; i < nmat; ++i) tot += rot[i];
+            fprintf(stderr, "[jacobi] sweep %d: %ld rotated pairs (of %d per cycle), %d/%d matrices done\n", sweep, tot,
+                    n_cta * rounds, ndone, nmat);
+        }
         bool changed = false;
         for (int i = 0; i < nmat; ++i) {
             if (!done[i] && rot[i] == 0) {
@@ -593,13 +632,48 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
     JMat *d_mats = reinterpret_cast<JMat *>(work + L.off_mats);
     double *wf = reinterpret_cast<double *>(work);
     {
+        // orientation + pre-sort: orthogonalise the side whose Gram matrix is closer to diagonal (for square
+        // blocks), vectors ordered by descending norm (de Rijk); both from one pass over A.
+        int max_mn = 0;
+        for (auto &mt : L.mats) max_mn = std::max(max_mn, mt.m + mt.n);
+        svd_prep_kernel<<<dim3((unsigned)max_mn, (unsigned)nmat), 128, 0, st>>>(wf, d_mats, A);
+        B200_CHECK_LAUNCH();
+        std::vector<int> perm0((size_t)L.perm_elems + 1, 0);
+        std::vector<double> nr;
+        bool changed = false;
+        for (int i = 0; i < nmat; ++i) {
+            JMat &mt = L.mats[(size_t)i];
+            nr.resize((size_t)mt.m + mt.n);
+            B200_CUDA_CHECK(cudaMemcpyAsync(nr.data(), wf + mt.prep_off, nr.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+            B200_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (mt.m == mt.n) {
+                double r4 = 0.0, c4 = 0.0;
+                for (int r = 0; r < mt.m; ++r) r4 += nr[r] * nr[r];
+                for (int c = 0; c < mt.n; ++c) c4 += nr[mt.m + c] * nr[mt.m + c];
+                int tr = (c4 > r4) ? 1 : 0;
+                if (tr != mt.transposed) {
+                    mt.transposed = tr;
+                    changed = true;
+                }
+            }
+            const double *vn = mt.transposed ? nr.data() + mt.m : nr.data();
+            int *pp = perm0.data() + mt.perm_off;
+            std::iota(pp, pp + mt.q, 0);
+            std::stable_sort(pp, pp + mt.q, [&](int a, int b) { return vn[a] > vn[b]; });
+        }
+        if (changed)
+            B200_CUDA_CHECK(cudaMemcpyAsync(work + L.off_mats, L.mats.data(), (size_t)nmat * sizeof(JMat),
+                                            cudaMemcpyHostToDevice, st));
+        int *d_perm = reinterpret_cast<int *>(work + L.off_perm);
+        B200_CUDA_CHECK(cudaMemcpyAsync(d_perm, perm0.data(), perm0.size() * 4, cudaMemcpyHostToDevice, st));
         int64_t max_elems = 0;
         for (auto &mt : L.mats) max_elems = std::max<int64_t>(max_elems, (int64_t)mt.q * mt.p);
         int64_t gx = std::min<int64_t>(std::max<int64_t>(1, (max_elems + 1023) / 1024), 2048);
-        svd_init_kernel<<<dim3((unsigned)gx, (unsigned)nmat), 256, 0, st>>>(wf, d_mats, A);
+        svd_init_kernel<<<dim3((unsigned)gx, (unsigned)nmat), 256, 0, st>>>(wf, d_mats, d_perm, A);
         B200_CHECK_LAUNCH();
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));  // perm0 (host) must outlive the copy
     }
-    int rc = run_jacobi(L, work, st, info, 40);
+    int rc = run_jacobi(L, work, st, info, 60);
     if (rc) return rc;
     std::vector<int> perm;
     rc = sort_norms(L, work, st, false, perm);

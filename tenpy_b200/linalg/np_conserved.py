@@ -32,6 +32,7 @@ __all__ = ['QTYPE', 'ChargeInfo', 'LegCharge', 'LegPipe', 'Array', 'zeros', 'eye
            'inner', 'norm', 'svd', 'eigh', 'outer', 'trace', 'to_iterable_arrays', 'pinv', 'concatenate_qdata']
 
 _PLAN_CACHE = {}
+svd_stats = {'calls': 0, 'jacobi_sweeps': []}   # diagnostics: Jacobi sweeps used by each npc.svd call
 _PLAN_CACHE_MAX = 4096
 
 
@@ -1078,7 +1079,9 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
     bufU = backend.zeros(lay_U.size)
     bufV = backend.zeros(lay_V.size)
     bufS = backend.empty(int(s_off[-1]))
-    lib.block_svd(m, n, lay.offsets, u_off, s_off[:-1], v_off, a._buf, bufU, bufS, bufV)
+    info = lib.block_svd(m, n, lay.offsets, u_off, s_off[:-1], v_off, a._buf, bufU, bufS, bufV)
+    svd_stats['calls'] += 1
+    svd_stats['jacobi_sweeps'].append(int(np.max(info)))
     S = backend.to_host(bufS)
     if np.any(np.isnan(S)):
         raise ValueError('NaN in S')
