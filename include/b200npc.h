@@ -148,18 +148,32 @@ int b200_take_blocks_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t
 int b200_scale_axis_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t *task_host,
                         const double *S_dev, double *X, b200_stream_t stream);
 
+/* OUT[c] = sum_r X[r*ld + c]^2 for a row-major (rows x cols) matrix (leverage scores of the null-space
+ * completion in np_conserved.svd; no reference counterpart: LAPACK returns a complete basis by itself) */
+int b200_col_sqnorms_f64(int64_t rows, int64_t cols, int64_t ld, const double *X, double *OUT,
+                         b200_stream_t stream);
+
 /* ---- block-diagonal SVD / eigh ------------------------------------------------------------------- */
 /* Batched one-sided block-Jacobi SVD of nblocks independent row-major matrices A_i (m[i] x n[i]) at
  * a_off[i]: A_i = U_i diag(S_i) VT_i with k_i = min(m_i, n_i), S_i sorted descending,
  * U_i (m_i x k_i) at u_off[i], S_i at s_off[i], VT_i (k_i x n_i) at vt_off[i], all row-major.
  * A is not modified.  work_dev must hold b200_block_svd_worksize(...) bytes.  Synchronous on `stream`.
  * info_host[i] = number of Jacobi sweeps used (>0) or -1 if not converged.
+ * Numerically negligible directions (row norm <= 16 eps sqrt(max(m,n)) |A_i|_F, i.e. singular values that are
+ * zero to working precision) are deflated: their singular value is reported as found (tiny), the vector on the
+ * accumulated side is exact (orthonormal), the vector on the other side is left ZERO and must be filled with an
+ * orthonormal completion by the caller when it is needed (tenpy_b200.linalg.np_conserved.svd does).
+ * nact_host[i] (may be NULL) = number of significant directions (they come first), transposed_host[i] (may be
+ * NULL) = 1 if the zero vectors are columns of U_i, 0 if they are rows of VT_i.
  * replaces _svd_worker npc:4950 -> svd_robust.svd svd_robust.py:37 (LAPACK gesdd / gesvd). */
+/* switch the deflation of negligible directions in b200_block_svd_f64 on (default) / off; returns the old value */
+int b200_svd_set_deflation(int on);
 int64_t b200_block_svd_worksize(int64_t nblocks, const int64_t *m_host, const int64_t *n_host);
 int b200_block_svd_f64(int64_t nblocks, const int64_t *m_host, const int64_t *n_host,
                        const int64_t *a_off_host, const int64_t *u_off_host, const int64_t *s_off_host,
                        const int64_t *vt_off_host, const double *A, double *U, double *S, double *VT,
-                       void *work_dev, int64_t work_bytes, int32_t *info_host, b200_stream_t stream);
+                       void *work_dev, int64_t work_bytes, int32_t *info_host, int32_t *nact_host,
+                       int32_t *transposed_host, b200_stream_t stream);
 /* Batched symmetric eigen-decomposition of nblocks row-major symmetric matrices A_i (n[i] x n[i]):
  * A_i = V_i diag(W_i) V_i^T, W_i ascending, eigenvectors in the COLUMNS of V_i (row-major n x n).
  * replaces _eig_worker npc:5041 (np.linalg.eigh, LAPACK syevd). */

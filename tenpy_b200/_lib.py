@@ -58,9 +58,11 @@ _SIGNATURES = {
     'b200_copy_blocks_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp]),
     'b200_take_blocks_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp, c_vp]),
     'b200_scale_axis_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp]),
+    'b200_col_sqnorms_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'b200_svd_set_deflation': (ctypes.c_int, [ctypes.c_int]),
     'b200_block_svd_worksize': (c_i64, [c_i64, c_i64p, c_i64p]),
     'b200_block_svd_f64': (ctypes.c_int, [c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_vp, c_vp, c_vp,
-                                          c_vp, c_vp, c_i64, c_i32p, c_vp]),
+                                          c_vp, c_vp, c_i64, c_i32p, c_i32p, c_i32p, c_vp]),
     'b200_block_eigh_worksize': (c_i64, [c_i64, c_i64p]),
     'b200_block_eigh_f64': (ctypes.c_int, [c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_vp, c_vp, c_vp, c_vp, c_i64,
                                            c_i32p, c_vp]),
@@ -232,8 +234,9 @@ class DeviceLib:
 
     def grouped_gemm(self, m, n, c_off, pair_ptr, k, a_off, b_off, A, B, C):
         ms, ns, cs, pp, ks, ao, bo = [_i64(x) for x in (m, n, c_off, pair_ptr, k, a_off, b_off)]
-        self._check(self.c.b200_grouped_gemm_f64(len(ms[0]), ms[1], ns[1], cs[1], pp[1], len(ks[0]), ks[1], ao[1],
-                                                 bo[1], _ptr(A), _ptr(B), _ptr(C), self.stream()))
+        with _Prof(self, 'gemm'):
+            self._check(self.c.b200_grouped_gemm_f64(len(ms[0]), ms[1], ns[1], cs[1], pp[1], len(ks[0]), ks[1], ao[1],
+                                                     bo[1], _ptr(A), _ptr(B), _ptr(C), self.stream()))
 
     # -- BLAS-1
     def axpy(self, n, alpha, X, Y):
@@ -289,11 +292,21 @@ class DeviceLib:
         wbytes = int(self.c.b200_block_svd_worksize(nb, ms[1], ns[1]))
         work = self.torch.empty(wbytes, dtype=self.torch.uint8, device=self.device)
         info = np.zeros(nb, dtype=np.int32)
+        nact = np.zeros(nb, dtype=np.int32)
+        transp = np.zeros(nb, dtype=np.int32)
         with _Prof(self, 'svd'):
             self._check(self.c.b200_block_svd_f64(nb, ms[1], ns[1], ao[1], uo[1], so[1], vo[1], _ptr(A), _ptr(U),
                                                   _ptr(S), _ptr(VT), _ptr(work), wbytes, info.ctypes.data_as(c_i32p),
+                                                  nact.ctypes.data_as(c_i32p), transp.ctypes.data_as(c_i32p),
                                                   self.stream()))
-        return info
+        return info, nact, transp
+
+    def col_sqnorms(self, rows, cols, ld, X, OUT):
+        with _Prof(self, 'svd'):
+            self._check(self.c.b200_col_sqnorms_f64(rows, cols, ld, _ptr(X), _ptr(OUT), self.stream()))
+
+    def svd_set_deflation(self, on):
+        return int(self.c.b200_svd_set_deflation(1 if on else 0))
 
     def block_eigh(self, n, a_off, w_off, v_off, A, W, V):
         ns, ao, wo, vo = [_i64(x) for x in (n, a_off, w_off, v_off)]

@@ -87,9 +87,32 @@ __global__ void __launch_bounds__(MV_THREADS) scale_axis_kernel(const int64_t *_
     }
 }
 
+// out[c] = sum_r X[r*ld + c]^2 : one thread per column, coalesced across the warp
+__global__ void __launch_bounds__(MV_THREADS) col_sqnorms_kernel(int64_t rows, int64_t cols, int64_t ld,
+                                                                 const double *__restrict__ x,
+                                                                 double *__restrict__ out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double s = 0.0;
+    for (int64_t r = 0; r < rows; ++r) {
+        double v = x[r * ld + c];
+        s = fma(v, v, s);
+    }
+    out[c] = s;
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_col_sqnorms_f64(int64_t rows, int64_t cols, int64_t ld, const double *X, double *OUT,
+                                    b200_stream_t stream) {
+    if (cols <= 0) return B200_OK;
+    col_sqnorms_kernel<<<(unsigned)((cols + MV_THREADS - 1) / MV_THREADS), MV_THREADS, 0, (cudaStream_t)stream>>>(
+        rows, cols, ld, X, OUT);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
 
 extern "C" int b200_copy_blocks_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t *task_host,
                                     const double *SRC, double *DST, b200_stream_t stream) {

@@ -45,7 +45,10 @@ struct JMat {
     int32_t transposed;                    // Y = A^T
     int32_t cta_begin;                     // first CTA of this matrix in a round launch
     int32_t perm_off;                      // offset into the int32 permutation pool
-    int32_t pad;
+    int32_t nb_act;                        // active row blocks (even, >= 2): logical rows [0, nb_act*JB)
+    int32_t rmap_off;                      // offset into the int32 row-map pool (logical row -> physical row)
+    int32_t n_act;                         // number of non-deflated vectors
+    double defl;                           // deflation threshold: rows with norm <= defl are negligible
     double shift;                          // eigh: diagonal shift
 };
 
@@ -53,13 +56,13 @@ constexpr int jacobi_smem_bytes() {
     return (2 * JP * JLDP + 2 * JP * JLDG + JP * JLDQT) * (int)sizeof(double) + 256;
 }
 
-__device__ __forceinline__ void j_load_chunk(double *sP, const double *base, int ld, int rowA0, int rowB0, int col0,
+__device__ __forceinline__ void j_load_chunk(double *sP, const double *base, int ld, const int *prow, int col0,
                                              int tid) {
     constexpr int CH = JP * (JKC / 2);
 #pragma unroll
     for (int c = tid; c < CH; c += JTHREADS) {
         int r = c / (JKC / 2), cc = (c % (JKC / 2)) * 2;
-        int grow = r < JB ? rowA0 + r : rowB0 + r - JB;
+        int grow = prow[r];
         int gcol = col0 + cc;
         bool ok = gcol < ld;
         const double *src = ok ? base + (int64_t)grow * ld + gcol : base;
@@ -67,15 +70,15 @@ __device__ __forceinline__ void j_load_chunk(double *sP, const double *base, int
     }
 }
 
-// rows of `base` (ld) <- Q^T rows ; panel rows rowA0.., rowB0..
-__device__ __forceinline__ void j_apply(double *bufs, const double (&qa)[2][4][4], double *base, int ld, int rowA0,
-                                        int rowB0, int tid) {
+// rows of `base` (ld) <- Q^T rows ; prow[0..31] = physical rows of the panel
+__device__ __forceinline__ void j_apply(double *bufs, const double (&qa)[2][4][4], double *base, int ld,
+                                        const int *prow, int tid) {
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int nch = (ld + JKC - 1) / JKC;
-    j_load_chunk(bufs, base, ld, rowA0, rowB0, 0, tid);
+    j_load_chunk(bufs, base, ld, prow, 0, tid);
     cp_async_commit();
     for (int ch = 0; ch < nch; ++ch) {
-        if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, base, ld, rowA0, rowB0, (ch + 1) * JKC, tid);
+        if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, base, ld, prow, (ch + 1) * JKC, tid);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
@@ -103,7 +106,7 @@ __device__ __forceinline__ void j_apply(double *bufs, const double (&qa)[2][4][4
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         int pr = i * 16 + g + 8 * hh;
-                        int grow = pr < JB ? rowA0 + pr : rowB0 + pr - JB;
+                        int grow = prow[pr];
                         double *dst = base + (int64_t)grow * ld + col + 2 * t;
                         *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][2 * hh], acc[i][2 * hh + 1]);
                     }
@@ -117,7 +120,8 @@ __device__ __forceinline__ void j_apply(double *bufs, const double (&qa)[2][4][4
 
 __global__ void __launch_bounds__(JTHREADS)
     jacobi_round_kernel(double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
-                        int round, int *__restrict__ rot_count, const int *__restrict__ done, double tol_scale) {
+                        const int *__restrict__ rmap, int round, int *__restrict__ rot_count,
+                        const int *__restrict__ done, double tol_scale) {
     extern __shared__ __align__(16) double jsmem[];
     double *bufs = jsmem;                    // 2 * JP * JLDP
     double *sG = bufs + 2 * JP * JLDP;       // JP * JLDG
@@ -126,13 +130,15 @@ __global__ void __launch_bounds__(JTHREADS)
     __shared__ double cs_c[JB], cs_s[JB];
     __shared__ int pr_p[JB], pr_q[JB];
     __shared__ double red[32];
+    __shared__ int s_rows[JP];
 
     const int mi = cta_mat[blockIdx.x];
     if (done[mi]) return;
     const JMat mt = mats[mi];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int j = blockIdx.x - mt.cta_begin;
-    const int nb = mt.nb;
+    const int nb = mt.nb_act;   // deflated (negligible) rows live in the blocks >= nb_act and are never touched
+    if (2 * j >= nb) return;
     int ba, bb;
     {
         const int nr = nb - 1;
@@ -150,7 +156,8 @@ __global__ void __launch_bounds__(JTHREADS)
             bb = tmp;
         }
     }
-    const int rowA0 = ba * JB, rowB0 = bb * JB;
+    if (tid < JP) s_rows[tid] = rmap[mt.rmap_off + (tid < JB ? ba * JB + tid : bb * JB + tid - JB)];
+    __syncthreads();
     double *Y = work + mt.y_off;
     double *W = work + mt.w_off;
     const int ld = mt.ldy;
@@ -160,10 +167,10 @@ __global__ void __launch_bounds__(JTHREADS)
         const int tm = warp >> 2, tn = warp & 3;  // 2 x 4 tiles of 16 x 8
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         const int nch = (ld + JKC - 1) / JKC;
-        j_load_chunk(bufs, Y, ld, rowA0, rowB0, 0, tid);
+        j_load_chunk(bufs, Y, ld, s_rows, 0, tid);
         cp_async_commit();
         for (int ch = 0; ch < nch; ++ch) {
-            if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, Y, ld, rowA0, rowB0, (ch + 1) * JKC, tid);
+            if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, Y, ld, s_rows, (ch + 1) * JKC, tid);
             cp_async_commit();
             cp_async_wait<1>();
             __syncthreads();
@@ -314,8 +321,8 @@ __global__ void __launch_bounds__(JTHREADS)
             qa[i][k8][2] = ap[4];
             qa[i][k8][3] = ap[8 * JLDQT + 4];
         }
-    j_apply(bufs, qa, Y, ld, rowA0, rowB0, tid);
-    j_apply(bufs, qa, W, mt.ldw, rowA0, rowB0, tid);
+    j_apply(bufs, qa, Y, ld, s_rows, tid);
+    j_apply(bufs, qa, W, mt.ldw, s_rows, tid);
 }
 
 // ---- init / finalize kernels ---------------------------------------------------------------------
@@ -419,7 +426,7 @@ __global__ void __launch_bounds__(128)
     if (r >= k) return;
     const int src = perm[mt.perm_off + r];
     const double s = work[mt.snorm_off + src];
-    const double inv = s > 0.0 ? 1.0 / s : 0.0;
+    const double inv = (s > mt.defl && s > 0.0) ? 1.0 / s : 0.0;   // negligible direction: filled by the caller
     const double *y = work + mt.y_off + (int64_t)src * mt.ldy;
     const double *w = work + mt.w_off + (int64_t)src * mt.ldw;
     if (threadIdx.x == 0) S[mt.s_off + r] = s;
@@ -454,10 +461,10 @@ struct JLayout {
     std::vector<JMat> mats;
     std::vector<int> cta_mat;
     int64_t f64_elems = 0;     // doubles in the work area
-    int64_t perm_elems = 0;
+    int64_t perm_elems = 0, rmap_elems = 0;
     int max_q = 0, max_nb = 0;
     // byte offsets of the integer regions inside the work buffer
-    int64_t off_mats = 0, off_cta = 0, off_rot = 0, off_done = 0, off_perm = 0, total_bytes = 0;
+    int64_t off_mats = 0, off_cta = 0, off_rot = 0, off_done = 0, off_perm = 0, off_rmap = 0, total_bytes = 0;
 };
 
 static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -466,7 +473,7 @@ static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, boo
     L.mats.resize((size_t)nblocks);
     int64_t off = 0;
     int cta = 0;
-    int64_t perm = 0;
+    int64_t perm = 0, rmap = 0;
     for (int64_t i = 0; i < nblocks; ++i) {
         JMat &mt = L.mats[(size_t)i];
         memset(&mt, 0, sizeof(JMat));
@@ -495,11 +502,17 @@ static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, boo
         cta += nb / 2;
         mt.perm_off = (int32_t)perm;
         perm += mt.q;
+        mt.rmap_off = (int32_t)rmap;
+        rmap += mt.qp;
+        mt.nb_act = nb;
+        mt.n_act = mt.q;
+        mt.defl = 0.0;
         L.max_q = std::max(L.max_q, (int)mt.q);
         L.max_nb = std::max(L.max_nb, nb);
     }
     L.f64_elems = off;
     L.perm_elems = perm;
+    L.rmap_elems = rmap;
     int64_t b = rup(off * (int64_t)sizeof(double), 256);
     L.off_mats = b;
     b += rup((int64_t)nblocks * (int64_t)sizeof(JMat), 256);
@@ -511,16 +524,24 @@ static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, boo
     b += rup(nblocks * 4, 256);
     L.off_perm = b;
     b += rup(perm * 4 + 4, 256);
+    L.off_rmap = b;
+    b += rup(rmap * 4 + 4, 256);
     L.total_bytes = b;
 }
 
-static int run_jacobi(const JLayout &L, char *work, cudaStream_t st, int32_t *info, int max_sweeps) {
+// Host driver of the Jacobi iteration.  After every sweep the row norms are read back (q doubles per
+// matrix): rows whose norm fell below the deflation threshold `defl` are numerically zero singular
+// directions -- they are moved (logically, through the row map) behind the active rows and never touched
+// again, so a numerically rank-deficient block only iterates on its significant rows.  Active rows are kept
+// ordered by descending norm (de Rijk).
+static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, int max_sweeps) {
     const int nmat = (int)L.mats.size();
     double *wf = reinterpret_cast<double *>(work);
     JMat *d_mats = reinterpret_cast<JMat *>(work + L.off_mats);
     int *d_cta = reinterpret_cast<int *>(work + L.off_cta);
     int *d_rot = reinterpret_cast<int *>(work + L.off_rot);
     int *d_done = reinterpret_cast<int *>(work + L.off_done);
+    int *d_rmap = reinterpret_cast<int *>(work + L.off_rmap);
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -528,45 +549,91 @@ static int run_jacobi(const JLayout &L, char *work, cudaStream_t st, int32_t *in
         attr_set = true;
     }
     std::vector<int> rot((size_t)nmat), done((size_t)nmat, 0);
-    for (int i = 0; i < nmat; ++i) info[i] = -1;
+    std::vector<int> rmap((size_t)L.rmap_elems + 1, 0);
+    for (int i = 0; i < nmat; ++i) {
+        info[i] = -1;
+        const JMat &mt = L.mats[(size_t)i];
+        std::iota(rmap.begin() + mt.rmap_off, rmap.begin() + mt.rmap_off + mt.qp, 0);
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_rmap, rmap.data(), rmap.size() * 4, cudaMemcpyHostToDevice, st));
     const int n_cta = (int)L.cta_mat.size();
-    const int rounds = std::max(1, L.max_nb - 1);
-    const double tol_scale = 4.0e-16;
+    const double tol_scale = 2.0e-15;   // tol = tol_scale * sqrt(p): a few times the rounding noise of a length-p dot product
+    const bool debug = getenv("B200_JACOBI_DEBUG") != nullptr;
     B200_CUDA_CHECK(cudaMemsetAsync(d_done, 0, (size_t)nmat * 4, st));
     int ndone = 0;
+    int round_counter = 0;
+    std::vector<double> nrm;
+    std::vector<int> order;
     for (int sweep = 0; sweep < max_sweeps && ndone < nmat; ++sweep) {
+        int rounds = 1;
+        for (int i = 0; i < nmat; ++i)
+            if (!done[i]) rounds = std::max(rounds, L.mats[(size_t)i].nb_act - 1);
         B200_CUDA_CHECK(cudaMemsetAsync(d_rot, 0, (size_t)nmat * 4, st));
         for (int r = 0; r < rounds; ++r) {
-            jacobi_round_kernel<<<n_cta, JTHREADS, jacobi_smem_bytes(), st>>>(wf, d_mats, d_cta, sweep * rounds + r,
+            jacobi_round_kernel<<<n_cta, JTHREADS, jacobi_smem_bytes(), st>>>(wf, d_mats, d_cta, d_rmap, round_counter++,
                                                                             d_rot, d_done, tol_scale);
             B200_CHECK_LAUNCH();
         }
+        jacobi_norms_kernel<<<dim3((unsigned)std::max(1, L.max_q), (unsigned)nmat), 128, 0, st>>>(wf, d_mats);
+        B200_CHECK_LAUNCH();
         B200_CUDA_CHECK(cudaMemcpyAsync(rot.data(), d_rot, (size_t)nmat * 4, cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (getenv("B200_JACOBI_DEBUG")) {
-            long tot = 0;
-            for (int i = 0; i < nmat; ++i) tot += rot[i];
-            fprintf(stderr, "[jacobi] sweep %d: %ld rotated pairs (of %d per cycle), %d/%d matrices done\n", sweep, tot,
-                    n_cta * rounds, ndone, nmat);
-        }
-        bool changed = false;
+        bool changed = false, mats_changed = false, remap = false;
+        long tot = 0;
         for (int i = 0; i < nmat; ++i) {
-            if (!done[i] && rot[i] == 0) {
+            tot += rot[i];
+            if (done[i]) continue;
+            JMat &mt = L.mats[(size_t)i];
+            if (rot[i] == 0) {
                 done[i] = 1;
                 info[i] = sweep + 1;
                 ++ndone;
                 changed = true;
+                continue;
             }
+            if (mt.defl <= 0.0) continue;
+            // re-order the logical rows: active rows by descending norm, then the deflated ones
+            nrm.resize((size_t)mt.q);
+            B200_CUDA_CHECK(cudaMemcpy(nrm.data(), wf + mt.snorm_off, (size_t)mt.q * sizeof(double), cudaMemcpyDeviceToHost));
+            order.resize((size_t)mt.q);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nrm[a] > nrm[b]; });
+            int n_act = 0;
+            while (n_act < mt.q && nrm[order[n_act]] > mt.defl) ++n_act;
+            int nb_act = (n_act + JB - 1) / JB;
+            if (nb_act < 2) nb_act = 2;
+            if (nb_act & 1) ++nb_act;
+            if (nb_act > mt.nb) nb_act = mt.nb;
+            int *rm = rmap.data() + mt.rmap_off;
+            // physical padding rows (>= q) stay at the very end of the logical order
+            for (int k = 0; k < mt.q; ++k) rm[k] = order[k];
+            for (int k = mt.q; k < mt.qp; ++k) rm[k] = k;
+            if (nb_act != mt.nb_act || n_act != mt.n_act) {
+                mt.nb_act = nb_act;
+                mt.n_act = n_act;
+                mats_changed = true;
+            }
+            remap = true;
         }
-        if (changed && ndone < nmat)
-            B200_CUDA_CHECK(cudaMemcpyAsync(d_done, done.data(), (size_t)nmat * 4, cudaMemcpyHostToDevice, st));
+        if (debug)
+            fprintf(stderr, "[jacobi] sweep %d: %ld rotated pairs, %d rounds, %d/%d matrices done, n_act[0]=%d/%d\n", sweep,
+                    tot, rounds, ndone, nmat, L.mats[0].n_act, L.mats[0].q);
+        if (ndone < nmat) {
+            if (changed)
+                B200_CUDA_CHECK(cudaMemcpyAsync(d_done, done.data(), (size_t)nmat * 4, cudaMemcpyHostToDevice, st));
+            if (mats_changed)   // (never for eigh: its device-side `shift` must not be overwritten)
+                B200_CUDA_CHECK(cudaMemcpyAsync(d_mats, L.mats.data(), (size_t)nmat * sizeof(JMat), cudaMemcpyHostToDevice, st));
+            if (remap)
+                B200_CUDA_CHECK(cudaMemcpyAsync(d_rmap, rmap.data(), rmap.size() * 4, cudaMemcpyHostToDevice, st));
+            B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
     }
     (void)d_cta;
     return B200_OK;
 }
 
 // sort (descending by norm) on the host; returns permutation pool
-static int sort_norms(const JLayout &L, char *work, cudaStream_t st, bool ascending, std::vector<int> &perm) {
+static int sort_norms(JLayout &L, char *work, cudaStream_t st, bool ascending, std::vector<int> &perm) {
     const int nmat = (int)L.mats.size();
     double *wf = reinterpret_cast<double *>(work);
     JMat *d_mats = reinterpret_cast<JMat *>(work + L.off_mats);
@@ -576,11 +643,16 @@ static int sort_norms(const JLayout &L, char *work, cudaStream_t st, bool ascend
     perm.assign((size_t)L.perm_elems + 1, 0);
     std::vector<double> nrm;
     for (int i = 0; i < nmat; ++i) {
-        const JMat &mt = L.mats[(size_t)i];
+        JMat &mt = L.mats[(size_t)i];
         nrm.resize((size_t)mt.q);
         B200_CUDA_CHECK(cudaMemcpyAsync(nrm.data(), wf + mt.snorm_off, (size_t)mt.q * sizeof(double),
                                         cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (mt.defl > 0.0) {   // number of significant (non-negligible) directions
+            int na = 0;
+            for (int k = 0; k < mt.q; ++k) na += (nrm[k] > mt.defl) ? 1 : 0;
+            mt.n_act = na;
+        }
         int *pp = perm.data() + mt.perm_off;
         std::iota(pp, pp + mt.q, 0);
         if (ascending)
@@ -597,6 +669,13 @@ static int sort_norms(const JLayout &L, char *work, cudaStream_t st, bool ascend
 
 using namespace b200;
 
+static int g_svd_deflation = 1;
+extern "C" int b200_svd_set_deflation(int on) {
+    int old = g_svd_deflation;
+    g_svd_deflation = on ? 1 : 0;
+    return old;
+}
+
 extern "C" int64_t b200_block_svd_worksize(int64_t nblocks, const int64_t *m, const int64_t *n) {
     if (nblocks <= 0) return 256;
     JLayout L;
@@ -607,7 +686,7 @@ extern "C" int64_t b200_block_svd_worksize(int64_t nblocks, const int64_t *m, co
 extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64_t *n, const int64_t *a_off,
                                   const int64_t *u_off, const int64_t *s_off, const int64_t *vt_off, const double *A,
                                   double *U, double *S, double *VT, void *work_dev, int64_t work_bytes,
-                                  int32_t *info, b200_stream_t stream) {
+                                  int32_t *info, int32_t *nact_host, int32_t *transposed_host, b200_stream_t stream) {
     if (nblocks <= 0) return B200_OK;
     if (nblocks > 65535) return set_error(B200_ERR_ARG, "too many blocks for one SVD batch");
     cudaStream_t st = (cudaStream_t)stream;
@@ -646,6 +725,12 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
             nr.resize((size_t)mt.m + mt.n);
             B200_CUDA_CHECK(cudaMemcpyAsync(nr.data(), wf + mt.prep_off, nr.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
             B200_CUDA_CHECK(cudaStreamSynchronize(st));
+            {
+                double fro2 = 0.0;
+                for (int r = 0; r < mt.m; ++r) fro2 += nr[r];
+                mt.defl = g_svd_deflation ? 16.0 * 2.220446049250313e-16 * sqrt((double)mt.p) * sqrt(fro2) : 0.0;
+                changed = true;
+            }
             if (mt.m == mt.n) {
                 double r4 = 0.0, c4 = 0.0;
                 for (int r = 0; r < mt.m; ++r) r4 += nr[r] * nr[r];
@@ -682,6 +767,10 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
         wf, d_mats, reinterpret_cast<int *>(work + L.off_perm), U, S, VT);
     B200_CHECK_LAUNCH();
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < nmat; ++i) {
+        if (nact_host) nact_host[i] = L.mats[(size_t)i].n_act;
+        if (transposed_host) transposed_host[i] = L.mats[(size_t)i].transposed;
+    }
     for (int i = 0; i < nmat; ++i)
         if (info[i] < 0) return set_error(B200_ERR_NOCONV, "block Jacobi SVD did not converge for block %d", i);
     return B200_OK;

@@ -1079,9 +1079,25 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
     bufU = backend.zeros(lay_U.size)
     bufV = backend.zeros(lay_V.size)
     bufS = backend.empty(int(s_off[-1]))
-    info = lib.block_svd(m, n, lay.offsets, u_off, s_off[:-1], v_off, a._buf, bufU, bufS, bufV)
+    info, nact, transp = lib.block_svd(m, n, lay.offsets, u_off, s_off[:-1], v_off, a._buf, bufU, bufS, bufV)
     svd_stats['calls'] += 1
     svd_stats['jacobi_sweeps'].append(int(np.max(info)))
+    if np.any(nact < k):
+        # numerically rank-deficient blocks: the kernel left the vectors of the negligible directions on one side
+        # zero; complete them to an orthonormal basis (LAPACK returns a complete basis, reference npc:4950)
+        try:
+            for i in np.nonzero(nact < k)[0]:
+                _fill_null_vectors(lib, int(m[i]), int(n[i]), int(k[i]), int(nact[i]), bool(transp[i]),
+                                   bufU, int(u_off[i]), bufV, int(v_off[i]))
+            svd_stats['completions'] = svd_stats.get('completions', 0) + 1
+        except _CompletionFailed:
+            old = lib.svd_set_deflation(False)
+            try:
+                bufU.zero_()
+                bufV.zero_()
+                info, nact, transp = lib.block_svd(m, n, lay.offsets, u_off, s_off[:-1], v_off, a._buf, bufU, bufS, bufV)
+            finally:
+                lib.svd_set_deflation(old)
     S = backend.to_host(bufS)
     if np.any(np.isnan(S)):
         raise ValueError('NaN in S')
@@ -1105,6 +1121,90 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
     U.iset_leg_labels([a_labels[0], labL])
     VH.iset_leg_labels([labR, a_labels[1]])
     return U, S, VH
+
+
+class _CompletionFailed(Exception):
+    pass
+
+
+def _strided_copy(lib, src, soff, dst, doff, shape, sstride, dstride):
+    rec = np.zeros((1, 22), dtype=np.int64)
+    r = len(shape)
+    rec[0, 0], rec[0, 1], rec[0, 2], rec[0, 3] = soff, doff, int(np.prod(shape)), r
+    rec[0, 4:10] = 1
+    rec[0, 4:4 + r] = shape
+    rec[0, 10:10 + r] = sstride
+    rec[0, 16:16 + r] = dstride
+    lib.copy_blocks(rec, backend.to_device(rec), src, dst)
+
+
+def _gemm(lib, mm, nn, kk, A, B, C):
+    lib.grouped_gemm([mm], [nn], [0], [0, 1], [kk], [0], [0], A, B, C)
+
+
+def _null_space_completion(lib, V, r, p, kf):
+    """`kf` orthonormal rows (device buffer, kf x p row-major) orthogonal to the `r` orthonormal rows of `V`.
+
+    Start from projected unit vectors ``X0 = E_sel - C^T V`` with ``C = V[:, sel]`` for the `kf` coordinates of
+    smallest leverage (so that ``X0 X0^T = 1 - C^T C`` is well conditioned), then orthonormalise with
+    Newton-Schulz iterations ``X <- (1 - D/2) X``, ``D = X X^T - 1`` -- GEMMs only (grouped FP64 tensor-core
+    kernel).  Left multiplications keep the rows inside the orthogonal complement of `V`."""
+    ones = backend.to_device(np.ones(1))
+    X = backend.zeros(kf * p)
+    if r > 0:
+        lev = backend.empty(p)
+        lib.col_sqnorms(r, p, p, V, lev)
+        sel = np.sort(np.argsort(backend.to_host(lev), kind='stable')[:kf]).astype(np.int64)
+        C = backend.empty(r * kf)
+        rec = np.array([[0, 0, r, kf, 1, p, 0]], dtype=np.int64)
+        lib.take_blocks(rec, backend.to_device(rec), backend.to_device(sel), V, C)
+        CT = backend.empty(kf * r)
+        _strided_copy(lib, C, 0, CT, 0, [kf, r], [1, kf], [r, 1])
+        _gemm(lib, kf, p, r, CT, V, X)
+        lib.scal(kf * p, -1., X)
+    else:
+        sel = np.arange(kf, dtype=np.int64)
+    seg = np.stack([np.zeros(kf, np.int64), np.arange(kf, dtype=np.int64) * p + sel, np.ones(kf, np.int64)], axis=1)
+    for s0 in range(0, kf, 32768):
+        part = np.ascontiguousarray(seg[s0:s0 + 32768])
+        lib.axpy_segments(len(part), backend.to_device(part), 1, 1., ones, X)
+    if r == 0:
+        return X
+    dseg = np.stack([np.zeros(kf, np.int64), np.arange(kf, dtype=np.int64) * (kf + 1), np.ones(kf, np.int64)], axis=1)
+    dseg_dev = [backend.to_device(np.ascontiguousarray(dseg[s0:s0 + 32768])) for s0 in range(0, kf, 32768)]
+    XT = backend.empty(kf * p)
+    G = backend.empty(kf * kf)
+    DX = backend.empty(kf * p)
+    out = backend.scalar_out()
+    for it in range(60):
+        _strided_copy(lib, X, 0, XT, 0, [p, kf], [1, p], [kf, 1])
+        _gemm(lib, kf, kf, p, X, XT, G)
+        for dsd in dseg_dev:
+            lib.axpy_segments(dsd.shape[0], dsd, 1, -1., ones, G)
+        lib.dot(kf * kf, G, G, backend.dot_scratch(), out)
+        err = float(np.sqrt(backend.read_scalar(out)))
+        if not np.isfinite(err) or (it == 0 and err > np.sqrt(kf) * (1. - 1e-7)):
+            raise _CompletionFailed('ill-conditioned start')
+        if err < 1e-13 * max(1., np.sqrt(kf)):
+            return X
+        _gemm(lib, kf, p, kf, G, X, DX)
+        lib.axpy(kf * p, -0.5, DX, X)
+    raise _CompletionFailed('Newton-Schulz did not converge')
+
+
+def _fill_null_vectors(lib, m, n, k, r, transposed, bufU, u_off, bufV, v_off):
+    """fill the zero vectors left by the deflating SVD kernel for block (m x n), see b200_block_svd_f64"""
+    kf = k - r
+    if not transposed:           # rows r..k-1 of VT (k x n) are missing; the first r rows are orthonormal
+        V = bufV[v_off:v_off + max(r, 1) * n]
+        X = _null_space_completion(lib, V, r, n, kf)
+        bufV[v_off + r * n:v_off + k * n].copy_(X[:kf * n])
+    else:                        # columns r..k-1 of U (m x k) are missing
+        V = backend.empty(max(r, 1) * m)
+        if r > 0:
+            _strided_copy(lib, bufU, u_off, V, 0, [r, m], [1, k], [m, 1])
+        X = _null_space_completion(lib, V, r, m, kf)
+        _strided_copy(lib, X, 0, bufU, u_off + r, [kf, m], [m, 1], [1, k])
 
 
 def pinv(a, cutoff=1.e-15):

@@ -20,16 +20,15 @@ for n in [int(x) for x in sys.argv[2:]]:
         h1 = rng.standard_normal((n, n)); h1 = (h1 + h1.T) / np.sqrt(n)
         h2 = rng.standard_normal((n, n)); h2 = (h2 + h2.T) / np.sqrt(n)
         A = A + 0.05 * (h1 * S[None, :] * S[:, None]) @ A @ h2
-    dA = backend.to_device(A.ravel())
-    dU, dS, dV = backend.zeros(n*n), backend.zeros(n), backend.zeros(n*n)
+    from tenpy_b200.linalg import np_conserved as npc
+    a = npc.Array.from_ndarray_trivial(A)
     torch.cuda.synchronize(); t0 = time.time()
     try:
-        info = lib.block_svd([n],[n],[0],[0],[0],[0], dA, dU, dS, dV)
+        Ua, S, Va = npc.svd(a)
     except Exception as e:
         print(n, 'FAILED', e); continue
     torch.cuda.synchronize(); dt = time.time()-t0
-    S = backend.to_host(dS); U = backend.to_host(dU).reshape(n,n); V = backend.to_host(dV).reshape(n,n)
+    U = Ua.to_ndarray(); V = Va.to_ndarray()
     Sref = np.linalg.svd(A, compute_uv=False)
-    k = int(np.sum(Sref > 1e-13 * Sref[0]))
-    print(kind, n, 'sweeps', info[0], 'time %.1f ms' % (dt*1e3), 'dS', np.abs(S-Sref).max(), 'rec', np.abs(U@np.diag(S)@V-A).max(),
-          'orthU(k=%d)' % k, np.abs(U[:, :k].T@U[:, :k]-np.eye(k)).max(), 'orthV', np.abs(V@V.T-np.eye(n)).max(), flush=True)
+    print(kind, n, 'sweeps', npc.svd_stats['jacobi_sweeps'][-1], 'time %.1f ms' % (dt*1e3), 'dS', np.abs(S-Sref).max(), 'rec', np.abs(U@np.diag(S)@V-A).max(),
+          'orthU', np.abs(U.T@U-np.eye(n)).max(), 'orthV', np.abs(V@V.T-np.eye(n)).max(), 'completions', npc.svd_stats.get('completions'), flush=True)

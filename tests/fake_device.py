@@ -125,17 +125,46 @@ class FakeDeviceLib:
             v = x[off:off + outer * ln * inner].reshape(outer, ln, inner)
             v *= s[soff:soff + ln][None, :, None]
 
+    deflation = True
+
+    def svd_set_deflation(self, on):
+        old, self.deflation = self.deflation, bool(on)
+        return int(old)
+
     def block_svd(self, m, n, a_off, u_off, s_off, vt_off, A, U, S, VT):
+        """numpy SVD; emulates the kernel's deflation contract (zero VT rows for negligible directions)"""
         self._count('block_svd')
         a, u, s, vt = A.numpy(), U.numpy(), S.numpy(), VT.numpy()
+        nact = np.zeros(len(m), dtype=np.int32)
         for i in range(len(m)):
             mi, ni = int(m[i]), int(n[i])
             k = min(mi, ni)
-            uu, ss, vv = np.linalg.svd(a[a_off[i]:a_off[i] + mi * ni].reshape(mi, ni), full_matrices=False)
+            blk = a[a_off[i]:a_off[i] + mi * ni].reshape(mi, ni)
+            uu, ss, vv = np.linalg.svd(blk, full_matrices=False)
+            defl = 16 * 2.220446049250313e-16 * np.sqrt(max(mi, ni)) * np.linalg.norm(blk) if self.deflation else -1.
+            r = int(np.sum(ss > defl))
+            vv = vv.copy()
+            vv[r:] = 0.
+            nact[i] = r
             u[u_off[i]:u_off[i] + mi * k] = uu.reshape(-1)
             s[s_off[i]:s_off[i] + k] = ss
             vt[vt_off[i]:vt_off[i] + k * ni] = vv.reshape(-1)
-        return np.ones(len(m), dtype=np.int32)
+        return np.ones(len(m), dtype=np.int32), nact, np.zeros(len(m), dtype=np.int32)
+
+    def col_sqnorms(self, rows, cols, ld, X, OUT):
+        self._count('col_sqnorms')
+        OUT.numpy()[:cols] = np.sum(X.numpy()[:rows * ld].reshape(rows, ld)[:, :cols]**2, axis=0)
+
+    def grouped_gemm(self, m, n, c_off, pair_ptr, k, a_off, b_off, A, B, C):
+        self._count('grouped_gemm')
+        a, b, c = A.numpy(), B.numpy(), C.numpy()
+        for t in range(len(m)):
+            mm, nn = int(m[t]), int(n[t])
+            acc = np.zeros((mm, nn))
+            for p in range(pair_ptr[t], pair_ptr[t + 1]):
+                kk = int(k[p])
+                acc += a[a_off[p]:a_off[p] + mm * kk].reshape(mm, kk) @ b[b_off[p]:b_off[p] + kk * nn].reshape(kk, nn)
+            c[c_off[t]:c_off[t] + mm * nn] = acc.reshape(-1)
 
     def block_eigh(self, n, a_off, w_off, v_off, A, W, V):
         self._count('block_eigh')

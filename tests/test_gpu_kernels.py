@@ -93,7 +93,8 @@ def test_block_svd(gpu_lib, shape):
     A = rng.standard_normal((m, n))
     dA = _dev(A.ravel())
     dU, dS, dV = backend.zeros(m * k), backend.zeros(k), backend.zeros(k * n)
-    info = gpu_lib.block_svd([m], [n], [0], [0], [0], [0], dA, dU, dS, dV)
+    info, nact, _ = gpu_lib.block_svd([m], [n], [0], [0], [0], [0], dA, dU, dS, dV)
+    assert nact[0] == k
     U = backend.to_host(dU).reshape(m, k)
     S = backend.to_host(dS)
     VT = backend.to_host(dV).reshape(k, n)
