@@ -573,14 +573,56 @@ extern "C" int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m, const in
         pairs[p].k = (int32_t)k[p];
         pairs[p].pad = 0;
     }
+    // descriptors go to a persistent grow-only device scratch (no cudaMalloc/cudaFree per call)
+    static char *scratch = nullptr;
+    static size_t scratch_cap = 0;
+    static int scratch_dev = -1;
+    TileSet ts;
+    build_tiles(tasks, pairs, ts);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t b_tasks = al(tasks.size() * sizeof(GemmTask)), b_pairs = al(pairs.size() * sizeof(GemmPair));
+    size_t b_tiles[3], total = b_tasks + b_pairs;
+    for (int c = 0; c < 3; ++c) {
+        b_tiles[c] = al(ts.tiles[c].size() * sizeof(GemmTile));
+        total += b_tiles[c];
+    }
+    int dev = 0;
+    B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != scratch_dev || total > scratch_cap) {
+        if (scratch && dev == scratch_dev) cudaFree(scratch);
+        scratch_cap = std::max<size_t>(total * 2, (size_t)1 << 20);
+        B200_CUDA_CHECK(cudaMalloc(&scratch, scratch_cap));
+        scratch_dev = dev;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
     DeviceGemmDesc d;
-    int rc = upload_desc(tasks, pairs, d);
-    if (rc == B200_OK) rc = run_desc(d, A, B, C, (cudaStream_t)stream);
+    d.device = dev;
+    char *at = scratch;
+    d.tasks = reinterpret_cast<GemmTask *>(at);
+    B200_CUDA_CHECK(cudaMemcpyAsync(at, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, st));
+    at += b_tasks;
+    d.pairs = reinterpret_cast<GemmPair *>(at);
+    B200_CUDA_CHECK(cudaMemcpyAsync(at, pairs.data(), pairs.size() * sizeof(GemmPair), cudaMemcpyHostToDevice, st));
+    at += b_pairs;
+    for (int c = 0; c < 3; ++c) {
+        d.n_tiles[c] = (int)ts.tiles[c].size();
+        d.tiles[c] = reinterpret_cast<GemmTile *>(at);
+        if (d.n_tiles[c])
+            B200_CUDA_CHECK(cudaMemcpyAsync(at, ts.tiles[c].data(), ts.tiles[c].size() * sizeof(GemmTile),
+                                            cudaMemcpyHostToDevice, st));
+        at += b_tiles[c];
+    }
+    bool vec = true;
+    for (auto &t : tasks)
+        if ((t.n & 1) || (t.c_off & 1)) vec = false;
+    for (auto &p : pairs)
+        if ((p.k & 1) || (p.a_off & 1) || (p.b_off & 1)) vec = false;
+    d.vec = vec;
+    int rc = run_desc(d, A, B, C, st);
     if (rc == B200_OK) {
-        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        cudaError_t e = cudaStreamSynchronize(st);   // host staging vectors and the scratch are reused afterwards
         if (e != cudaSuccess) rc = set_error(B200_ERR_CUDA, "grouped gemm failed: %s", cudaGetErrorString(e));
     }
-    d.release();
     return rc;
 }
 

@@ -200,13 +200,15 @@ __global__ void __launch_bounds__(JTHREADS)
     __syncthreads();
 
     // ---- convergence measure of this pair ----
+    const double defl2 = mt.defl * mt.defl;
     double offmax = 0.0;
     for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
         int r = idx / JP, c = idx % JP;
         if (r < c) {
-            double d = sG[r * JLDG + r] * sG[c * JLDG + c];
+            const double drr = sG[r * JLDG + r], dcc = sG[c * JLDG + c];
+            double d = drr * dcc;
             double o = fabs(sG[r * JLDG + c]);
-            if (d > 0.0) {
+            if (drr > defl2 && dcc > defl2) {   // negligible (deflated) rows are inert
                 double v = o / sqrt(d);
                 offmax = fmax(offmax, v);
             }
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(JTHREADS)
                 double gpp = sG[p * JLDG + p], gqq = sG[q * JLDG + q], gpq = sG[p * JLDG + q];
                 double c = 1.0, s = 0.0;
                 double lim = tol_in * sqrt(fabs(gpp * gqq));
-                if (fabs(gpq) > lim && fabs(gpq) > 0.0) {
+                if (fabs(gpq) > lim && gpp > defl2 && gqq > defl2) {
                     // t = tan(theta) of the Jacobi rotation: one sqrt, one division, one rsqrt
                     const double aa = gqq - gpp, bb = 2.0 * gpq;
                     const double hh = sqrt(aa * aa + bb * bb);

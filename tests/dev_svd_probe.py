@@ -22,12 +22,14 @@ for n in [int(x) for x in sys.argv[2:]]:
         A = A + 0.05 * (h1 * S[None, :] * S[:, None]) @ A @ h2
     from tenpy_b200.linalg import np_conserved as npc
     a = npc.Array.from_ndarray_trivial(A)
+    lib.profile = {}
     torch.cuda.synchronize(); t0 = time.time()
     try:
         Ua, S, Va = npc.svd(a)
     except Exception as e:
         print(n, 'FAILED', e); continue
     torch.cuda.synchronize(); dt = time.time()-t0
+    print('   families', {k: (v[0], round(v[1], 2)) for k, v in lib.profile_summary().items()}); lib.profile = None
     U = Ua.to_ndarray(); V = Va.to_ndarray()
     Sref = np.linalg.svd(A, compute_uv=False)
     print(kind, n, 'sweeps', npc.svd_stats['jacobi_sweeps'][-1], 'time %.1f ms' % (dt*1e3), 'dS', np.abs(S-Sref).max(), 'rec', np.abs(U@np.diag(S)@V-A).max(),
