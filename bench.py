@@ -343,7 +343,9 @@ def run_b200(args):
             'matvec_gflops': roof['gemm']['achieved'] * 1e3, 'peaks': peaks_kind,
             'result': {'E': [float(x) for x in allst[:, 1]], 'S_mid': [float(x) for x in allst[:, 2]],
                        'N_lanczos_mean': N_lan, 'svd_jacobi_sweeps_mean': float(np.mean(jsw)),
-                       'svd_jacobi_sweeps_max': int(np.max(jsw))}}
+                       'svd_jacobi_sweeps_max': int(np.max(jsw)), 'svd_calls': svd_stats['calls'],
+                       'svd_warm_starts': svd_stats.get('guess_used', 0),
+                       'svd_null_space_completions': svd_stats.get('completions', 0)}}
     if not args.no_cpu:
         est = cpu_sweep_estimate(args, args.cpu_bonds)
         line['cpu_baseline'] = {'value': est['sweep_s'], 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',

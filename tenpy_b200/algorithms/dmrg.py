@@ -88,6 +88,10 @@ class TwoSiteDMRGEngine:
         self.sweeps = options.get('sweep_0', 0)
         self.time0 = time.time()
         self.mixer = None
+        # warm start of the Jacobi SVD with the singular vectors found at the same bond one update earlier
+        # (extension; 2 x (chi d)^2 doubles per bond stay resident in HBM)
+        self.svd_warm_start = options.get('svd_warm_start', True)
+        self._svd_guess = {}
         self.env = MPOEnvironment(psi, model.H_MPO, psi)
         self.eff_H = None
         self.i0 = 0
@@ -246,8 +250,11 @@ class TwoSiteDMRGEngine:
         update_LP, update_RP = self.update_LP_RP
         if self.mixer is None:
             qtotal_i0 = self.psi.get_B(i0, form=None).qtotal
+            full = [] if self.svd_warm_start else None
             U, S, VH, err, _ = svd_theta(theta, self.trunc_params, qtotal_LR=[qtotal_i0, None],
-                                         inner_labels=['vR', 'vL'])
+                                         inner_labels=['vR', 'vL'], guess=self._svd_guess.get(i0), full_out=full)
+            if full:
+                self._svd_guess[i0] = full[0]
             S_a = S
         else:
             old_BL_qtotal = self.psi.get_B(i0, form=None).qtotal

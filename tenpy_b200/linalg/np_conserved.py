@@ -1028,13 +1028,66 @@ def trace(a, leg1=0, leg2=1):
     return float(np.trace(a.to_ndarray()))
 
 
+def _guess_is_orthogonal_basis(G, leg, axis_keep, a_qind):
+    """True if the 2D Array `G` is block-wise square (a complete orthonormal basis change of `leg`) and covers
+    every sector of `leg` that `a` uses."""
+    if G is None or G.rank != 2:
+        return False
+    try:
+        G.legs[axis_keep].test_equal(leg)
+    except ValueError:
+        return False
+    lay = G._layout
+    if lay.nblocks == 0 or np.any(lay.shapes[:, 0] != lay.shapes[:, 1]):
+        return False
+    if G.shape[0] != G.shape[1]:
+        return False
+    have = set(lay.qdata[:, axis_keep].tolist())
+    return all(q in have for q in set(a_qind.tolist()))
+
+
 def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, None], inner_labels=[None, None],
-        inner_qconj=+1):
+        inner_qconj=+1, guess=None):
     """Singular value decomposition ``a = U diag(S) VH`` of a 2D Array (reference npc:3676).
 
     All charge blocks are decomposed by ONE batched block-Jacobi launch sequence on the device
     (replaces the per-block LAPACK loop of npc:4950).  `S` is block-ordered, descending within a block,
-    exactly like the reference's."""
+    exactly like the reference's.
+
+    `guess` (extension, optional): ``(U_guess, VH_guess)`` complete orthonormal bases from an earlier SVD of a
+    nearby matrix (e.g. the same DMRG bond one sweep ago).  The matrix is rotated into that basis first
+    (two extra GEMMs), which makes the Jacobi iteration start almost converged; the result is a full SVD of
+    `a` to the usual tolerance whatever the quality of the guess."""
+    if guess is not None and compute_uv and cutoff is None and not full_matrices and a.rank == 2:
+        Ug, VHg = guess
+        chinfo = a.chinfo
+        qtotal_L, qtotal_R = qtotal_LR
+        if qtotal_L is None and qtotal_R is None:
+            qtotal_R = a.qtotal
+        if qtotal_L is None:
+            qtotal_L = chinfo.make_valid(a.qtotal - qtotal_R)
+        elif qtotal_R is None:
+            qtotal_R = chinfo.make_valid(a.qtotal - qtotal_L)
+        qtotal_L, qtotal_R = chinfo.make_valid(qtotal_L), chinfo.make_valid(qtotal_R)
+        if a.legs[0].is_blocked() and a.legs[1].is_blocked() and a._layout.nblocks:
+            if _guess_is_orthogonal_basis(Ug, a.legs[0], 0, a._layout.qdata[:, 0]):
+                a2 = tensordot(Ug.conj(), a, axes=[0, 0])
+                a2.iset_leg_labels([None, a._labels[1]])
+                U2, S, VH = svd(a2, qtotal_LR=[chinfo.make_valid(qtotal_L - Ug.qtotal), qtotal_R],
+                                inner_labels=inner_labels, inner_qconj=inner_qconj)
+                U = tensordot(Ug, U2, axes=[1, 0])
+                U.iset_leg_labels([a._labels[0], inner_labels[0]])
+                svd_stats['guess_used'] = svd_stats.get('guess_used', 0) + 1
+                return U, S, VH
+            if _guess_is_orthogonal_basis(VHg, a.legs[1], 1, a._layout.qdata[:, 1]):
+                a2 = tensordot(a, VHg.conj(), axes=[1, 1])
+                a2.iset_leg_labels([a._labels[0], None])
+                U, S, VH2 = svd(a2, qtotal_LR=[qtotal_L, chinfo.make_valid(qtotal_R - VHg.qtotal)],
+                                inner_labels=inner_labels, inner_qconj=inner_qconj)
+                VH = tensordot(VH2, VHg, axes=[1, 0])
+                VH.iset_leg_labels([inner_labels[1], a._labels[1]])
+                svd_stats['guess_used'] = svd_stats.get('guess_used', 0) + 1
+                return U, S, VH
     if a.rank != 2:
         raise ValueError('SVD is only defined for a 2D matrix. Use LegPipes!')
     if full_matrices:

@@ -107,11 +107,16 @@ def truncate(S, options):
     return mask, norm_new, TruncationError.from_S(S[np.logical_not(mask)])
 
 
-def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL']):
+def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'], guess=None, full_out=None):
     """SVD of the matrix `theta` and truncation (reference truncation.py:258).
 
-    Returns ``(U, S, VH, err, renormalization)`` with ``theta ~= U diag(S * renormalization) VH``."""
-    U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR, inner_labels=inner_labels)
+    Returns ``(U, S, VH, err, renormalization)`` with ``theta ~= U diag(S * renormalization) VH``.
+    Extensions: `guess` is handed to :func:`npc.svd` (warm start); if `full_out` is a list, the untruncated
+    ``(U, VH)`` are appended to it (shallow copies, to be used as the next guess)."""
+    U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR, inner_labels=inner_labels,
+                       guess=guess)
+    if full_out is not None:
+        full_out.append((U.copy(deep=False), VH.copy(deep=False)))
     renormalization = np.linalg.norm(S)
     S = S / renormalization
     piv, new_norm, err = truncate(S, trunc_par)
