@@ -168,6 +168,10 @@ int b200_col_sqnorms_f64(int64_t rows, int64_t cols, int64_t ld, const double *X
  * replaces _svd_worker npc:4950 -> svd_robust.svd svd_robust.py:37 (LAPACK gesdd / gesvd). */
 /* switch the deflation of negligible directions in b200_block_svd_f64 on (default) / off; returns the old value */
 int b200_svd_set_deflation(int on);
+/* additional deflation threshold relative to |A_i|_F (default 0 = rounding level only): directions with a
+ * singular value below tol_rel*|A_i|_F are treated like the negligible ones; returns the old value.  A DMRG
+ * truncation discards them anyway (the reference's `svd_min`, truncation.py:196). */
+double b200_svd_set_deflation_tol(double tol_rel);
 int64_t b200_block_svd_worksize(int64_t nblocks, const int64_t *m_host, const int64_t *n_host);
 int b200_block_svd_f64(int64_t nblocks, const int64_t *m_host, const int64_t *n_host,
                        const int64_t *a_off_host, const int64_t *u_off_host, const int64_t *s_off_host,

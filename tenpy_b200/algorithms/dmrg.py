@@ -146,6 +146,10 @@ class TwoSiteDMRGEngine:
             return False
         if self.mixer is not None:
             return False
+        if any(isinstance(s, npc.Array) for s in self.psi._S):
+            # a sweep with the mixer leaves 2-D bond matrices; one mixer-free sweep restores the diagonal form
+            # (the reference does this with Sweep.mixer_cleanup, mps_common.py:693)
+            return False
         E = self.sweep_stats['E']
         S = self.sweep_stats['S']
         Delta_E = (E[-1] - E[-2]) / self.N_sweeps_check

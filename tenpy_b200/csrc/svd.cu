@@ -672,6 +672,12 @@ static int sort_norms(JLayout &L, char *work, cudaStream_t st, bool ascending, s
 using namespace b200;
 
 static int g_svd_deflation = 1;
+static double g_svd_defl_rel = 0.0;   // additional relative deflation threshold (0: only the rounding-level one)
+extern "C" double b200_svd_set_deflation_tol(double tol_rel) {
+    double old = g_svd_defl_rel;
+    g_svd_defl_rel = tol_rel > 0.0 ? tol_rel : 0.0;
+    return old;
+}
 extern "C" int b200_svd_set_deflation(int on) {
     int old = g_svd_deflation;
     g_svd_deflation = on ? 1 : 0;
@@ -730,7 +736,7 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
             {
                 double fro2 = 0.0;
                 for (int r = 0; r < mt.m; ++r) fro2 += nr[r];
-                mt.defl = g_svd_deflation ? 16.0 * 2.220446049250313e-16 * sqrt((double)mt.p) * sqrt(fro2) : 0.0;
+                mt.defl = g_svd_deflation ? std::max(16.0 * 2.220446049250313e-16 * sqrt((double)mt.p), g_svd_defl_rel) * sqrt(fro2) : 0.0;
                 changed = true;
             }
             if (mt.m == mt.n) {

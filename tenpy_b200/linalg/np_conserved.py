@@ -1047,7 +1047,7 @@ def _guess_is_orthogonal_basis(G, leg, axis_keep, a_qind):
 
 
 def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, None], inner_labels=[None, None],
-        inner_qconj=+1, guess=None):
+        inner_qconj=+1, guess=None, deflation_tol=None):
     """Singular value decomposition ``a = U diag(S) VH`` of a 2D Array (reference npc:3676).
 
     All charge blocks are decomposed by ONE batched block-Jacobi launch sequence on the device
@@ -1057,7 +1057,16 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
     `guess` (extension, optional): ``(U_guess, VH_guess)`` complete orthonormal bases from an earlier SVD of a
     nearby matrix (e.g. the same DMRG bond one sweep ago).  The matrix is rotated into that basis first
     (two extra GEMMs), which makes the Jacobi iteration start almost converged; the result is a full SVD of
-    `a` to the usual tolerance whatever the quality of the guess."""
+    `a` to the usual tolerance whatever the quality of the guess.
+    `deflation_tol` (extension, optional): see ``b200_svd_set_deflation_tol`` in include/b200npc.h; ``None``
+    keeps the library default (rounding level only, LAPACK-grade factorisation)."""
+    if deflation_tol is not None:
+        lib0 = backend.get_lib()
+        old_tol = lib0.svd_set_deflation_tol(deflation_tol)
+        try:
+            return svd(a, full_matrices, compute_uv, cutoff, qtotal_LR, inner_labels, inner_qconj, guess, None)
+        finally:
+            lib0.svd_set_deflation_tol(old_tol)
     if guess is not None and compute_uv and cutoff is None and not full_matrices and a.rank == 2:
         Ug, VHg = guess
         chinfo = a.chinfo

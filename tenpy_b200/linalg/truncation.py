@@ -112,9 +112,13 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
 
     Returns ``(U, S, VH, err, renormalization)`` with ``theta ~= U diag(S * renormalization) VH``.
     Extensions: `guess` is handed to :func:`npc.svd` (warm start); if `full_out` is a list, the untruncated
-    ``(U, VH)`` are appended to it (shallow copies, to be used as the next guess)."""
+    ``(U, VH)`` are appended to it (shallow copies, to be used as the next guess).  Option
+    ``trunc_par['svd_deflation_tol']`` (default 1e-10): singular directions below that fraction of ``|theta|``
+    are not iterated to convergence inside the Jacobi SVD -- their values are reported approximately
+    (absolute error below the tolerance) and their vectors are an orthonormal completion; the state changes by
+    at most that relative amount, the energy to second order in it."""
     U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR, inner_labels=inner_labels,
-                       guess=guess)
+                       guess=guess, deflation_tol=trunc_par.get('svd_deflation_tol', 1.e-10))
     if full_out is not None:
         full_out.append((U.copy(deep=False), VH.copy(deep=False)))
     renormalization = np.linalg.norm(S)

@@ -126,6 +126,11 @@ class FakeDeviceLib:
             v *= s[soff:soff + ln][None, :, None]
 
     deflation = True
+    deflation_tol = 0.
+
+    def svd_set_deflation_tol(self, tol_rel):
+        old, self.deflation_tol = self.deflation_tol, float(tol_rel)
+        return old
 
     def svd_set_deflation(self, on):
         old, self.deflation = self.deflation, bool(on)
@@ -141,7 +146,8 @@ class FakeDeviceLib:
             k = min(mi, ni)
             blk = a[a_off[i]:a_off[i] + mi * ni].reshape(mi, ni)
             uu, ss, vv = np.linalg.svd(blk, full_matrices=False)
-            defl = 16 * 2.220446049250313e-16 * np.sqrt(max(mi, ni)) * np.linalg.norm(blk) if self.deflation else -1.
+            defl = max(16 * 2.220446049250313e-16 * np.sqrt(max(mi, ni)), self.deflation_tol) * np.linalg.norm(blk) \
+                if self.deflation else -1.
             r = int(np.sum(ss > defl))
             vv = vv.copy()
             vv[r:] = 0.
