@@ -4,8 +4,9 @@
 set -x
 mkdir -p gpurun_out
 # 1. launch list of the bench command (per-launch device time; cold-cache + serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-60000} -c ${COUNT:-6000} --csv \
-    --log-file gpurun_out/r01_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu \
+# (bench.py brackets its timed steps with cudaProfilerStart/Stop, so only those launches are listed)
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c ${COUNT:-80000} --csv \
+    --log-file gpurun_out/r01_launches.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu \
     > gpurun_out/r01_launches_bench.log 2>&1
 # 2. full capture of the dominant GEMM (matvec, 128x128 tile config) and of the Jacobi round kernel
 ncu --set full --clock-control none --import-source on -k regex:grouped_gemm_kernel -s 6 -c 2 \

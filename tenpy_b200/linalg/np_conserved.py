@@ -1047,7 +1047,7 @@ def _guess_is_orthogonal_basis(G, leg, axis_keep, a_qind):
 
 
 def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, None], inner_labels=[None, None],
-        inner_qconj=+1, guess=None, deflation_tol=None):
+        inner_qconj=+1, guess=None, deflation_tol=None, n_keep=None):
     """Singular value decomposition ``a = U diag(S) VH`` of a 2D Array (reference npc:3676).
 
     All charge blocks are decomposed by ONE batched block-Jacobi launch sequence on the device
@@ -1059,12 +1059,14 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
     (two extra GEMMs), which makes the Jacobi iteration start almost converged; the result is a full SVD of
     `a` to the usual tolerance whatever the quality of the guess.
     `deflation_tol` (extension, optional): see ``b200_svd_set_deflation_tol`` in include/b200npc.h; ``None``
-    keeps the library default (rounding level only, LAPACK-grade factorisation)."""
+    keeps the library default (rounding level only, LAPACK-grade factorisation).
+    `n_keep` (extension, optional): the caller keeps at most that many singular triplets (``chi_max``); vectors of
+    negligible directions beyond it are not completed (they are zero, their `S` is exactly 0)."""
     if deflation_tol is not None:
         lib0 = backend.get_lib()
         old_tol = lib0.svd_set_deflation_tol(deflation_tol)
         try:
-            return svd(a, full_matrices, compute_uv, cutoff, qtotal_LR, inner_labels, inner_qconj, guess, None)
+            return svd(a, full_matrices, compute_uv, cutoff, qtotal_LR, inner_labels, inner_qconj, guess, None, n_keep)
         finally:
             lib0.svd_set_deflation_tol(old_tol)
     if guess is not None and compute_uv and cutoff is None and not full_matrices and a.rank == 2:
@@ -1083,7 +1085,7 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
                 a2 = tensordot(Ug.conj(), a, axes=[0, 0])
                 a2.iset_leg_labels([None, a._labels[1]])
                 U2, S, VH = svd(a2, qtotal_LR=[chinfo.make_valid(qtotal_L - Ug.qtotal), qtotal_R],
-                                inner_labels=inner_labels, inner_qconj=inner_qconj)
+                                inner_labels=inner_labels, inner_qconj=inner_qconj, n_keep=n_keep)
                 U = tensordot(Ug, U2, axes=[1, 0])
                 U.iset_leg_labels([a._labels[0], inner_labels[0]])
                 svd_stats['guess_used'] = svd_stats.get('guess_used', 0) + 1
@@ -1092,7 +1094,7 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
                 a2 = tensordot(a, VHg.conj(), axes=[1, 1])
                 a2.iset_leg_labels([a._labels[0], None])
                 U, S, VH2 = svd(a2, qtotal_LR=[qtotal_L, chinfo.make_valid(qtotal_R - VHg.qtotal)],
-                                inner_labels=inner_labels, inner_qconj=inner_qconj)
+                                inner_labels=inner_labels, inner_qconj=inner_qconj, n_keep=n_keep)
                 VH = tensordot(VH2, VHg, axes=[1, 0])
                 VH.iset_leg_labels([inner_labels[1], a._labels[1]])
                 svd_stats['guess_used'] = svd_stats.get('guess_used', 0) + 1
@@ -1147,12 +1149,19 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
     if np.any(nact < k):
         # numerically rank-deficient blocks: the kernel left the vectors of the negligible directions on one side
         # zero; complete them to an orthonormal basis (LAPACK returns a complete basis, reference npc:4950)
+        n_fill = np.zeros(len(k), dtype=np.int64)
         try:
             for i in np.nonzero(nact < k)[0]:
-                _fill_null_vectors(lib, int(m[i]), int(n[i]), int(k[i]), int(nact[i]), bool(transp[i]),
-                                   bufU, int(u_off[i]), bufV, int(v_off[i]))
+                # the caller keeps at most `n_keep` vectors in total (svd_theta: chi_max): no need to complete more
+                k_fill = int(k[i]) if n_keep is None else min(int(k[i]), max(int(n_keep), int(nact[i])))
+                n_fill[i] = k_fill - int(nact[i])
+                if n_fill[i] > 0:
+                    _fill_null_vectors(lib, int(m[i]), int(n[i]), int(k[i]), int(nact[i]), int(n_fill[i]),
+                                       bool(transp[i]), bufU, int(u_off[i]), bufV, int(v_off[i]))
             svd_stats['completions'] = svd_stats.get('completions', 0) + 1
         except _CompletionFailed:
+            svd_stats['completion_fallbacks'] = svd_stats.get('completion_fallbacks', 0) + 1
+            n_fill = None
             old = lib.svd_set_deflation(False)
             try:
                 bufU.zero_()
@@ -1160,6 +1169,16 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
                 info, nact, transp = lib.block_svd(m, n, lay.offsets, u_off, s_off[:-1], v_off, a._buf, bufU, bufS, bufV)
             finally:
                 lib.svd_set_deflation(old)
+        if n_fill is not None:
+            # singular values of the negligible directions: tiny but positive for the completed vectors (so that a
+            # truncation prefers them), exactly zero for the ones left without a vector
+            S_h = backend.to_host(bufS).copy()
+            for i in np.nonzero(nact < k)[0]:
+                lo, hi = int(s_off[i]) + int(nact[i]), int(s_off[i]) + int(k[i])
+                mid = lo + int(n_fill[i])
+                S_h[lo:mid] = np.maximum(S_h[lo:mid], 1.e-99)
+                S_h[mid:hi] = 0.
+            bufS = backend.to_device(S_h)
     S = backend.to_host(bufS)
     if np.any(np.isnan(S)):
         raise ValueError('NaN in S')
@@ -1254,13 +1273,12 @@ def _null_space_completion(lib, V, r, p, kf):
     raise _CompletionFailed('Newton-Schulz did not converge')
 
 
-def _fill_null_vectors(lib, m, n, k, r, transposed, bufU, u_off, bufV, v_off):
-    """fill the zero vectors left by the deflating SVD kernel for block (m x n), see b200_block_svd_f64"""
-    kf = k - r
+def _fill_null_vectors(lib, m, n, k, r, kf, transposed, bufU, u_off, bufV, v_off):
+    """fill `kf` of the zero vectors left by the deflating SVD kernel for block (m x n), see b200_block_svd_f64"""
     if not transposed:           # rows r..k-1 of VT (k x n) are missing; the first r rows are orthonormal
         V = bufV[v_off:v_off + max(r, 1) * n]
         X = _null_space_completion(lib, V, r, n, kf)
-        bufV[v_off + r * n:v_off + k * n].copy_(X[:kf * n])
+        bufV[v_off + r * n:v_off + (r + kf) * n].copy_(X[:kf * n])
     else:                        # columns r..k-1 of U (m x k) are missing
         V = backend.empty(max(r, 1) * m)
         if r > 0:

@@ -118,7 +118,8 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
     (absolute error below the tolerance) and their vectors are an orthonormal completion; the state changes by
     at most that relative amount, the energy to second order in it."""
     U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR, inner_labels=inner_labels,
-                       guess=guess, deflation_tol=trunc_par.get('svd_deflation_tol', 1.e-10))
+                       guess=guess, deflation_tol=trunc_par.get('svd_deflation_tol', 1.e-10),
+                       n_keep=trunc_par.get('chi_max', 100))
     if full_out is not None:
         full_out.append((U.copy(deep=False), VH.copy(deep=False)))
     renormalization = np.linalg.norm(S)

@@ -224,9 +224,6 @@ class MPOEnvironment:
         S = self.ket.get_SR(i0)
         RP = self.get_RP(i0, store=False)
         if isinstance(S, npc.Array):
-            LP = npc.tensordot(LP, S, axes=['vR', 0]).ireplace_label(2, 'vR') if True else LP
-            LP = npc.tensordot(S.conj(), LP, axes=[0, 'vR*'])
-            LP = LP.itranspose([0, 1, 2])
-            return npc.inner(LP, RP, axes='range', do_conj=False)
+            raise NotImplementedError('full_contraction across a bond holding a 2-D mixer matrix')
         LP = LP.scale_axis(S, 'vR').iscale_axis(S, 'vR*')
         return npc.inner(LP, RP, axes=[['vR*', 'wR', 'vR'], ['vL*', 'wL', 'vL']], do_conj=False)
