@@ -753,6 +753,19 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
             int *pp = perm0.data() + mt.perm_off;
             std::iota(pp, pp + mt.q, 0);
             std::stable_sort(pp, pp + mt.q, [&](int a, int b) { return vn[a] > vn[b]; });
+            // vn = SQUARED norms: vectors that are negligible from the start never enter the active set
+            // (Y is filled in this order, so the active rows are the first n_act logical = physical rows)
+            if (mt.defl > 0.0) {
+                int n_act = 0;
+                while (n_act < mt.q && vn[pp[n_act]] > mt.defl * mt.defl) ++n_act;
+                int nb_act = (n_act + JB - 1) / JB;
+                if (nb_act < 2) nb_act = 2;
+                if (nb_act & 1) ++nb_act;
+                if (nb_act > mt.nb) nb_act = mt.nb;
+                mt.n_act = n_act;
+                mt.nb_act = nb_act;
+                changed = true;
+            }
         }
         if (changed)
             B200_CUDA_CHECK(cudaMemcpyAsync(work + L.off_mats, L.mats.data(), (size_t)nmat * sizeof(JMat),

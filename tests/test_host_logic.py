@@ -201,3 +201,44 @@ def test_mpo_matches_reference(fake_device):
     # the reference orders its MPO states differently (graph construction); compare invariants:
     assert got.shape == ref.shape
     assert abs(np.linalg.norm(got.to_dense()) - np.linalg.norm(ref.to_dense())) < 1e-12
+
+
+def test_svd_extensions_host_logic(fake_device):
+    """warm start (`guess`), deflation tolerance and `n_keep`: results stay a valid SVD / valid isometries"""
+    from tenpy_b200.linalg import np_conserved as npc
+    rng = np.random.default_rng(11)
+    g = h.load('reshape_svd.npz')
+    m = h.to_product(h.oarray_from(g, 'm'))
+    U0, S0, VH0 = npc.svd(m, inner_labels=['vR', 'vL'])
+    # a nearby matrix, decomposed with the previous vectors as guess
+    pert = h.to_product(h.oarray_from(g, 'm'))
+    pert.iscale_prefactor(1e-3)
+    m2 = m + pert
+    used = npc.svd_stats.get('guess_used', 0)
+    U, S, VH = npc.svd(m2, inner_labels=['vR', 'vL'], guess=(U0, VH0))
+    rec = npc.tensordot(U.scale_axis(S, 1), VH, axes=1)
+    assert npc.norm(rec - m2) < 1e-12 * npc.norm(m2)
+    Sd = np.linalg.svd(m2.to_ndarray(), compute_uv=False)
+    assert np.max(np.abs(np.sort(S)[::-1] - Sd[:len(S)])) < 1e-12
+    # rank deficient matrix: deflation + completion, all vectors vs only n_keep of them
+    A = rng.standard_normal((40, 12)) @ rng.standard_normal((12, 50))
+    a = npc.Array.from_ndarray_trivial(A, labels=['a', 'b'])
+    U, S, VH = npc.svd(a)
+    k = 40
+    assert np.max(np.abs(U.to_ndarray().T @ U.to_ndarray() - np.eye(k))) < 1e-12
+    assert np.max(np.abs(VH.to_ndarray() @ VH.to_ndarray().T - np.eye(k))) < 1e-12
+    assert np.max(np.abs(U.to_ndarray() @ np.diag(S) @ VH.to_ndarray() - A)) < 1e-12 * np.linalg.norm(A)
+    U, S, VH = npc.svd(a, n_keep=20)
+    Vd = VH.to_ndarray()
+    assert np.max(np.abs(Vd[:20] @ Vd[:20].T - np.eye(20))) < 1e-12 and np.all(Vd[20:] == 0.) and np.all(S[20:] == 0.)
+    assert np.all(S[12:20] > 0.)
+    # deflation tolerance: directions below 1e-6 |A| are replaced, the factorisation error stays below it
+    q1, _ = np.linalg.qr(rng.standard_normal((30, 30)))
+    q2, _ = np.linalg.qr(rng.standard_normal((30, 30)))
+    s = np.logspace(0, -12, 30)
+    B = (q1 * s) @ q2
+    b = npc.Array.from_ndarray_trivial(B)
+    U, S, VH = npc.svd(b, deflation_tol=1e-6)
+    assert np.max(np.abs(S - s)) < 2e-6
+    assert np.max(np.abs(U.to_ndarray() @ np.diag(S) @ VH.to_ndarray() - B)) < 1e-5
+    assert np.max(np.abs(VH.to_ndarray() @ VH.to_ndarray().T - np.eye(30))) < 1e-12
