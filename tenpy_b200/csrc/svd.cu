@@ -32,6 +32,7 @@ constexpr int JLDP = JKC + 4;   // smem row stride of a panel chunk
 constexpr int JTHREADS = 256;
 constexpr int JLDG = JP + 1;
 constexpr int JLDQT = JP + 4;
+constexpr int J_NSPLIT_MAX = 16;    // column splits of the streaming phases of one pair
 constexpr int J_INNER_SWEEPS = 4;   // the pivot block only has to be diagonalised "well enough" per round
 
 struct JMat {
@@ -52,9 +53,7 @@ struct JMat {
     double shift;                          // eigh: diagonal shift
 };
 
-constexpr int jacobi_smem_bytes() {
-    return (2 * JP * JLDP + 2 * JP * JLDG + JP * JLDQT) * (int)sizeof(double) + 256;
-}
+constexpr int jacobi_smem_bytes() { return 2 * JP * JLDP * (int)sizeof(double); }   // two panel chunks
 
 __device__ __forceinline__ void j_load_chunk(double *sP, const double *base, int ld, const int *prow, int col0,
                                              int tid) {
@@ -70,19 +69,21 @@ __device__ __forceinline__ void j_load_chunk(double *sP, const double *base, int
     }
 }
 
-// rows of `base` (ld) <- Q^T rows ; prow[0..31] = physical rows of the panel
+// rows of `base` (ld) <- Q^T rows for the column chunks ch0, ch0+chstep, ... ; prow[0..31] = physical rows
 __device__ __forceinline__ void j_apply(double *bufs, const double (&qa)[2][4][4], double *base, int ld,
-                                        const int *prow, int tid) {
+                                        const int *prow, int tid, int ch0, int chstep) {
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int nch = (ld + JKC - 1) / JKC;
-    j_load_chunk(bufs, base, ld, prow, 0, tid);
+    if (ch0 >= nch) return;
+    j_load_chunk(bufs, base, ld, prow, ch0 * JKC, tid);
     cp_async_commit();
-    for (int ch = 0; ch < nch; ++ch) {
-        if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, base, ld, prow, (ch + 1) * JKC, tid);
+    int it = 0;
+    for (int ch = ch0; ch < nch; ch += chstep, ++it) {
+        if (ch + chstep < nch) j_load_chunk(bufs + ((it + 1) & 1) * JP * JLDP, base, ld, prow, (ch + chstep) * JKC, tid);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const double *sp = bufs + (ch & 1) * JP * JLDP;
+        const double *sp = bufs + (it & 1) * JP * JLDP;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int nt = warp * 2 + h;
@@ -118,84 +119,115 @@ __device__ __forceinline__ void j_apply(double *bufs, const double (&qa)[2][4][4
     cp_async_wait<0>();
 }
 
-__global__ void __launch_bounds__(JTHREADS)
-    jacobi_round_kernel(double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
-                        const int *__restrict__ rmap, int round, int *__restrict__ rot_count,
-                        const int *__restrict__ done, double tol_scale) {
-    extern __shared__ __align__(16) double jsmem[];
-    double *bufs = jsmem;                    // 2 * JP * JLDP
-    double *sG = bufs + 2 * JP * JLDP;       // JP * JLDG
-    double *sQ = sG + JP * JLDG;             // JP * JLDG
-    double *sQT = sQ + JP * JLDG;            // JP * JLDQT
-    __shared__ double cs_c[JB], cs_s[JB];
-    __shared__ int pr_p[JB], pr_q[JB];
-    __shared__ double red[32];
-    __shared__ int s_rows[JP];
+// the 32 physical rows of pair `j` of matrix `mt` in round `round` (round-robin tournament over the active
+// blocks); returns false if this CTA has no pair.  Must be followed by __syncthreads().
+__device__ __forceinline__ bool j_pair_rows(const JMat &mt, int j, int round, const int *__restrict__ rmap,
+                                            int *s_rows, int tid) {
+    const int nb = mt.nb_act;   // deflated (negligible) rows live in the blocks >= nb_act and are never touched
+    if (2 * j >= nb) return false;
+    int ba, bb;
+    const int nr = nb - 1;
+    const int r = round % nr;
+    if (j == 0) {
+        ba = nb - 1;
+        bb = r;
+    } else {
+        ba = (r + j) % nr;
+        bb = (r - j + nr) % nr;
+    }
+    if (ba > bb) {
+        int tmp = ba;
+        ba = bb;
+        bb = tmp;
+    }
+    if (tid < JP) s_rows[tid] = rmap[mt.rmap_off + (tid < JB ? ba * JB + tid : bb * JB + tid - JB)];
+    return true;
+}
 
-    const int mi = cta_mat[blockIdx.x];
+// One Jacobi round = three launches, so that the streaming phases use the whole GPU:
+//   jacobi_gram_kernel  grid (nsplit, pairs): partial G = P P^T over a subset of the column chunks (DMMA),
+//                       one 32x32 partial per split in Gbuf[pair][split]
+//   jacobi_eig_kernel   grid (pairs): convergence test, parallel cyclic Jacobi on G in shared memory, Q^T (rows
+//                       ordered by descending eigenvalue) -> QTbuf[pair], flag[pair] = rotated
+//   jacobi_apply_kernel grid (nsplit, pairs, 2): P <- Q^T P (z = 0) and the same rows of W <- Q^T W (z = 1)
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_gram_kernel(const double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
+                       const int *__restrict__ rmap, int round, const int *__restrict__ done,
+                       double *__restrict__ Gbuf) {
+    extern __shared__ __align__(16) double jsmem[];
+    double *bufs = jsmem;   // 2 * JP * JLDP
+    __shared__ int s_rows[JP];
+    const int mi = cta_mat[blockIdx.y];
     if (done[mi]) return;
     const JMat mt = mats[mi];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int j = blockIdx.x - mt.cta_begin;
-    const int nb = mt.nb_act;   // deflated (negligible) rows live in the blocks >= nb_act and are never touched
-    if (2 * j >= nb) return;
-    int ba, bb;
-    {
-        const int nr = nb - 1;
-        const int r = round % nr;
-        if (j == 0) {
-            ba = nb - 1;
-            bb = r;
-        } else {
-            ba = (r + j) % nr;
-            bb = (r - j + nr) % nr;
-        }
-        if (ba > bb) {
-            int tmp = ba;
-            ba = bb;
-            bb = tmp;
-        }
-    }
-    if (tid < JP) s_rows[tid] = rmap[mt.rmap_off + (tid < JB ? ba * JB + tid : bb * JB + tid - JB)];
+    if (!j_pair_rows(mt, blockIdx.y - mt.cta_begin, round, rmap, s_rows, tid)) return;
     __syncthreads();
-    double *Y = work + mt.y_off;
-    double *W = work + mt.w_off;
+    const double *Y = work + mt.y_off;
     const int ld = mt.ldy;
-
-    // ---- phase 1: G = P P^T ----
-    {
-        const int tm = warp >> 2, tn = warp & 3;  // 2 x 4 tiles of 16 x 8
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        const int nch = (ld + JKC - 1) / JKC;
-        j_load_chunk(bufs, Y, ld, s_rows, 0, tid);
+    const int nch = (ld + JKC - 1) / JKC;
+    const int ch0 = blockIdx.x, chstep = gridDim.x;
+    if (ch0 >= nch) return;
+    const int tm = warp >> 2, tn = warp & 3;  // 2 x 4 tiles of 16 x 8
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    j_load_chunk(bufs, Y, ld, s_rows, ch0 * JKC, tid);
+    cp_async_commit();
+    int it = 0;
+    for (int ch = ch0; ch < nch; ch += chstep, ++it) {
+        if (ch + chstep < nch) j_load_chunk(bufs + ((it + 1) & 1) * JP * JLDP, Y, ld, s_rows, (ch + chstep) * JKC, tid);
         cp_async_commit();
-        for (int ch = 0; ch < nch; ++ch) {
-            if (ch + 1 < nch) j_load_chunk(bufs + ((ch + 1) & 1) * JP * JLDP, Y, ld, s_rows, (ch + 1) * JKC, tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-            __syncthreads();
-            const double *sp = bufs + (ch & 1) * JP * JLDP;
+        cp_async_wait<1>();
+        __syncthreads();
+        const double *sp = bufs + (it & 1) * JP * JLDP;
 #pragma unroll
-            for (int k8 = 0; k8 < JKC / 8; ++k8) {
-                double af[4], bf[2];
-                const double *ap = sp + (tm * 16 + g) * JLDP + k8 * 8 + t;
-                af[0] = ap[0];
-                af[1] = ap[8 * JLDP];
-                af[2] = ap[4];
-                af[3] = ap[8 * JLDP + 4];
-                const double *bp = sp + (tn * 8 + g) * JLDP + k8 * 8 + t;
-                bf[0] = bp[0];
-                bf[1] = bp[4];
-                dmma_16x8x8(acc, af, bf);
-            }
-            __syncthreads();
+        for (int k8 = 0; k8 < JKC / 8; ++k8) {
+            double af[4], bf[2];
+            const double *ap = sp + (tm * 16 + g) * JLDP + k8 * 8 + t;
+            af[0] = ap[0];
+            af[1] = ap[8 * JLDP];
+            af[2] = ap[4];
+            af[3] = ap[8 * JLDP + 4];
+            const double *bp = sp + (tn * 8 + g) * JLDP + k8 * 8 + t;
+            bf[0] = bp[0];
+            bf[1] = bp[4];
+            dmma_16x8x8(acc, af, bf);
         }
-        cp_async_wait<0>();
-        const int r0 = tm * 16 + g, c0 = tn * 8 + 2 * t;
-        sG[r0 * JLDG + c0] = acc[0];
-        sG[r0 * JLDG + c0 + 1] = acc[1];
-        sG[(r0 + 8) * JLDG + c0] = acc[2];
-        sG[(r0 + 8) * JLDG + c0 + 1] = acc[3];
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    // partial result of this column split (summed in a fixed order by jacobi_eig_kernel: deterministic)
+    double *G = Gbuf + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (JP * JP);
+    const int r0 = tm * 16 + g, c0 = tn * 8 + 2 * t;
+    G[r0 * JP + c0] = acc[0];
+    G[r0 * JP + c0 + 1] = acc[1];
+    G[(r0 + 8) * JP + c0] = acc[2];
+    G[(r0 + 8) * JP + c0 + 1] = acc[3];
+}
+
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_eig_kernel(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
+                      const int *__restrict__ done, double tol_scale, const double *__restrict__ Gbuf, int nsplit,
+                      double *__restrict__ QTbuf, int *__restrict__ flags) {
+    __shared__ double sG[JP * JLDG];
+    __shared__ double sQ[JP * JLDG];
+    __shared__ double cs_c[JB], cs_s[JB];
+    __shared__ int pr_p[JB], pr_q[JB];
+    __shared__ double red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) flags[blockIdx.x] = 0;
+    const int mi = cta_mat[blockIdx.x];
+    if (done[mi]) return;
+    const JMat mt = mats[mi];
+    if (2 * (blockIdx.x - mt.cta_begin) >= mt.nb_act) return;
+    {
+        const int nch = (mt.ldy + JKC - 1) / JKC;
+        const int ns = nsplit < nch ? nsplit : nch;
+        const double *G = Gbuf + (int64_t)blockIdx.x * nsplit * (JP * JP);
+        for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+            double v = 0.0;
+            for (int sp = 0; sp < ns; ++sp) v += G[sp * (JP * JP) + idx];
+            sG[(idx / JP) * JLDG + (idx % JP)] = v;
+        }
     }
     __syncthreads();
 
@@ -303,28 +335,44 @@ __global__ void __launch_bounds__(JTHREADS)
         sG[tid * JLDG + JP] = (double)rk;
     }
     __syncthreads();
-    // sQT[rank(i)][k] = Q[k][i]   (row `rank(i)` of Q^T, sorted)
+    double *QT = QTbuf + (int64_t)blockIdx.x * (JP * JP);
     for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
         int i = idx / JP, k = idx % JP;
         int rk = (int)sG[i * JLDG + JP];
-        sQT[rk * JLDQT + k] = sQ[k * JLDG + i];
+        QT[rk * JP + k] = sQ[k * JLDG + i];
     }
-    __syncthreads();
+    if (tid == 0) flags[blockIdx.x] = 1;
+}
 
-    // ---- phase 3: P <- Q^T P, W rows <- Q^T W rows ----
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_apply_kernel(double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
+                        const int *__restrict__ rmap, int round, const double *__restrict__ QTbuf,
+                        const int *__restrict__ flags) {
+    extern __shared__ __align__(16) double jsmem[];
+    double *bufs = jsmem;   // 2 * JP * JLDP
+    __shared__ int s_rows[JP];
+    if (!flags[blockIdx.y]) return;
+    const int mi = cta_mat[blockIdx.y];
+    const JMat mt = mats[mi];
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    if (!j_pair_rows(mt, blockIdx.y - mt.cta_begin, round, rmap, s_rows, tid)) return;
+    __syncthreads();
+    const double *QT = QTbuf + (int64_t)blockIdx.y * (JP * JP);
     double qa[2][4][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int k8 = 0; k8 < 4; ++k8) {
-            const double *ap = sQT + (i * 16 + g) * JLDQT + k8 * 8 + t;
+            const double *ap = QT + (i * 16 + g) * JP + k8 * 8 + t;
             qa[i][k8][0] = ap[0];
-            qa[i][k8][1] = ap[8 * JLDQT];
+            qa[i][k8][1] = ap[8 * JP];
             qa[i][k8][2] = ap[4];
-            qa[i][k8][3] = ap[8 * JLDQT + 4];
+            qa[i][k8][3] = ap[8 * JP + 4];
         }
-    j_apply(bufs, qa, Y, ld, s_rows, tid);
-    j_apply(bufs, qa, W, mt.ldw, s_rows, tid);
+    if (blockIdx.z == 0)
+        j_apply(bufs, qa, work + mt.y_off, mt.ldy, s_rows, tid, blockIdx.x, gridDim.x);
+    else
+        j_apply(bufs, qa, work + mt.w_off, mt.ldw, s_rows, tid, blockIdx.x, gridDim.x);
 }
 
 // ---- init / finalize kernels ---------------------------------------------------------------------
@@ -464,6 +512,8 @@ struct JLayout {
     std::vector<int> cta_mat;
     int64_t f64_elems = 0;     // doubles in the work area
     int64_t perm_elems = 0, rmap_elems = 0;
+    int64_t g_off = 0, qt_off = 0;   // f64 offsets of the per-pair Gram partials and Q^T matrices
+    int64_t off_flags = 0;
     int max_q = 0, max_nb = 0;
     // byte offsets of the integer regions inside the work buffer
     int64_t off_mats = 0, off_cta = 0, off_rot = 0, off_done = 0, off_perm = 0, off_rmap = 0, total_bytes = 0;
@@ -512,6 +562,10 @@ static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, boo
         L.max_q = std::max(L.max_q, (int)mt.q);
         L.max_nb = std::max(L.max_nb, nb);
     }
+    L.g_off = off;
+    off += (int64_t)L.cta_mat.size() * J_NSPLIT_MAX * JP * JP;
+    L.qt_off = off;
+    off += (int64_t)L.cta_mat.size() * JP * JP;
     L.f64_elems = off;
     L.perm_elems = perm;
     L.rmap_elems = rmap;
@@ -528,6 +582,8 @@ static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, boo
     b += rup(perm * 4 + 4, 256);
     L.off_rmap = b;
     b += rup(rmap * 4 + 4, 256);
+    L.off_flags = b;
+    b += rup((int64_t)L.cta_mat.size() * 4 + 4, 256);
     L.total_bytes = b;
 }
 
@@ -544,9 +600,14 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
     int *d_rot = reinterpret_cast<int *>(work + L.off_rot);
     int *d_done = reinterpret_cast<int *>(work + L.off_done);
     int *d_rmap = reinterpret_cast<int *>(work + L.off_rmap);
+    double *d_G = wf + L.g_off;
+    double *d_QT = wf + L.qt_off;
+    int *d_flags = reinterpret_cast<int *>(work + L.off_flags);
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             jacobi_smem_bytes()));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              jacobi_smem_bytes()));
         attr_set = true;
     }
@@ -571,10 +632,26 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
         for (int i = 0; i < nmat; ++i)
             if (!done[i]) rounds = std::max(rounds, L.mats[(size_t)i].nb_act - 1);
         B200_CUDA_CHECK(cudaMemsetAsync(d_rot, 0, (size_t)nmat * 4, st));
+        // column splits: enough CTAs to fill the GPU ~3x with the pairs that are still active
+        int act_pairs = 0, max_ld = 0;
+        for (int i = 0; i < nmat; ++i)
+            if (!done[i]) {
+                act_pairs += L.mats[(size_t)i].nb_act / 2;
+                max_ld = std::max(max_ld, std::max(L.mats[(size_t)i].ldy, L.mats[(size_t)i].ldw));
+            }
+        int nsplit = (3 * sm_count() + act_pairs - 1) / std::max(1, act_pairs);
+        nsplit = std::max(1, std::min(nsplit, std::min(J_NSPLIT_MAX, (max_ld + JKC - 1) / JKC)));
         for (int r = 0; r < rounds; ++r) {
-            jacobi_round_kernel<<<n_cta, JTHREADS, jacobi_smem_bytes(), st>>>(wf, d_mats, d_cta, d_rmap, round_counter++,
-                                                                            d_rot, d_done, tol_scale);
+            jacobi_gram_kernel<<<dim3((unsigned)nsplit, (unsigned)n_cta), JTHREADS, jacobi_smem_bytes(), st>>>(
+                wf, d_mats, d_cta, d_rmap, round_counter, d_done, d_G);
             B200_CHECK_LAUNCH();
+            jacobi_eig_kernel<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit, d_QT,
+                                                        d_flags);
+            B200_CHECK_LAUNCH();
+            jacobi_apply_kernel<<<dim3((unsigned)nsplit, (unsigned)n_cta, 2), JTHREADS, jacobi_smem_bytes(), st>>>(
+                wf, d_mats, d_cta, d_rmap, round_counter, d_QT, d_flags);
+            B200_CHECK_LAUNCH();
+            ++round_counter;
         }
         jacobi_norms_kernel<<<dim3((unsigned)std::max(1, L.max_q), (unsigned)nmat), 128, 0, st>>>(wf, d_mats);
         B200_CHECK_LAUNCH();

@@ -116,10 +116,12 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
     ``trunc_par['svd_deflation_tol']`` (default 1e-10): singular directions below that fraction of ``|theta|``
     are not iterated to convergence inside the Jacobi SVD -- their values are reported approximately
     (absolute error below the tolerance) and their vectors are an orthonormal completion; the state changes by
-    at most that relative amount, the energy to second order in it."""
+    at most that relative amount, the energy to second order in it.  Without `full_out` only the vectors a
+    truncation can keep (``chi_max``) are completed; with it the bases are completed fully, because the next
+    warm start needs a complete orthonormal basis."""
     U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR, inner_labels=inner_labels,
                        guess=guess, deflation_tol=trunc_par.get('svd_deflation_tol', 1.e-10),
-                       n_keep=trunc_par.get('chi_max', 100))
+                       n_keep=(trunc_par.get('chi_max', 100) if full_out is None else None))
     if full_out is not None:
         full_out.append((U.copy(deep=False), VH.copy(deep=False)))
     renormalization = np.linalg.norm(S)
