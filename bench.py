@@ -290,6 +290,7 @@ def run_b200(args):
     S_mid = eng._entropy_approx[L // 2]
     N_lan = float(np.mean(eng.update_stats['N_lanczos'][-2 * (L - 2):]))
     from tenpy_b200.linalg.np_conserved import svd_stats
+    from tenpy_b200.linalg.truncation import subspace_stats as sub_stats
     jsw = svd_stats['jacobi_sweeps'][-2 * (L - 2):]
 
     # ---- end-to-end: the same sweep through the public API with HOST buffers (H2D + D2H inside the timer)
@@ -347,7 +348,10 @@ def run_b200(args):
                        'N_lanczos_mean': N_lan, 'svd_jacobi_sweeps_mean': float(np.mean(jsw)),
                        'svd_jacobi_sweeps_max': int(np.max(jsw)), 'svd_calls': svd_stats['calls'],
                        'svd_warm_starts': svd_stats.get('guess_used', 0),
-                       'svd_null_space_completions': svd_stats.get('completions', 0)}}
+                       'svd_null_space_completions': svd_stats.get('completions', 0),
+                       'svd_subspace_tried': sub_stats['tried'], 'svd_subspace_used': sub_stats['used'],
+                       'svd_subspace_residual_median': float(np.median(sub_stats['residuals'][-2 * (L - 2):]))
+                       if sub_stats['residuals'] else None}}
     if not args.no_cpu:
         est = cpu_sweep_estimate(args, args.cpu_bonds)
         line['cpu_baseline'] = {'value': est['sweep_s'], 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',

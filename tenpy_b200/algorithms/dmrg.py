@@ -88,9 +88,13 @@ class TwoSiteDMRGEngine:
         self.sweeps = options.get('sweep_0', 0)
         self.time0 = time.time()
         self.mixer = None
-        # warm start of the Jacobi SVD with the singular vectors found at the same bond one update earlier
-        # (extension; 2 x (chi d)^2 doubles per bond stay resident in HBM)
-        self.svd_warm_start = options.get('svd_warm_start', True)
+        # warm start of the Jacobi SVD from the previous update of the same bond (extension):
+        #   'subspace' (default): decompose theta inside the span of the previously kept isometry when the part
+        #                outside is below the truncation tolerance (truncation.svd_theta), no extra memory;
+        #   'full'     : rotate theta with the complete previous singular vector bases (2 (chi d)^2 doubles per bond);
+        #   False      : cold start every time.
+        ws = options.get('svd_warm_start', 'subspace')
+        self.svd_warm_start = 'full' if ws is True else ws
         self._svd_guess = {}
         self.env = MPOEnvironment(psi, model.H_MPO, psi)
         self.eff_H = None
@@ -254,11 +258,16 @@ class TwoSiteDMRGEngine:
         update_LP, update_RP = self.update_LP_RP
         if self.mixer is None:
             qtotal_i0 = self.psi.get_B(i0, form=None).qtotal
-            full = [] if self.svd_warm_start else None
+            ws = self.svd_warm_start
+            full = [] if ws == 'full' else None
             U, S, VH, err, _ = svd_theta(theta, self.trunc_params, qtotal_LR=[qtotal_i0, None],
-                                         inner_labels=['vR', 'vL'], guess=self._svd_guess.get(i0), full_out=full)
+                                         inner_labels=['vR', 'vL'],
+                                         guess=self._svd_guess.get(i0) if ws == 'full' else None, full_out=full,
+                                         subspace=self._svd_guess.get(i0) if ws == 'subspace' else None)
             if full:
                 self._svd_guess[i0] = full[0]
+            elif ws == 'subspace':
+                self._svd_guess[i0] = (U.copy(deep=False), VH.copy(deep=False))
             S_a = S
         else:
             old_BL_qtotal = self.psi.get_B(i0, form=None).qtotal

@@ -17,6 +17,7 @@
 //   sorted on the host (k doubles), vectors written by a final gather kernel.
 // Never produces NaN for finite input (the reference falls back gesdd->gesvd for that, npc:4971-4978).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <numeric>
 #include <vector>
@@ -775,6 +776,7 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
     if (nblocks <= 0) return B200_OK;
     if (nblocks > 65535) return set_error(B200_ERR_ARG, "too many blocks for one SVD batch");
     cudaStream_t st = (cudaStream_t)stream;
+    const double t_start = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     JLayout L;
     make_layout(nblocks, m, n, false, L);
     if (work_bytes < L.total_bytes) return set_error(B200_ERR_ARG, "SVD work buffer too small: %lld < %lld",
@@ -856,8 +858,12 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
         B200_CHECK_LAUNCH();
         B200_CUDA_CHECK(cudaStreamSynchronize(st));  // perm0 (host) must outlive the copy
     }
+    const bool dbg = getenv("B200_JACOBI_DEBUG") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_prep = now();
     int rc = run_jacobi(L, work, st, info, 60);
     if (rc) return rc;
+    const double t_jac = now();
     std::vector<int> perm;
     rc = sort_norms(L, work, st, false, perm);
     if (rc) return rc;
@@ -865,6 +871,9 @@ extern "C" int b200_block_svd_f64(int64_t nblocks, const int64_t *m, const int64
         wf, d_mats, reinterpret_cast<int *>(work + L.off_perm), U, S, VT);
     B200_CHECK_LAUNCH();
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (dbg)
+        fprintf(stderr, "[svd] prep+init %.2f ms, jacobi %.2f ms (%d sweeps), sort+finalize %.2f ms, n_act %d/%d\n",
+                t_prep - t_start, t_jac - t_prep, info[0], now() - t_jac, L.mats[0].n_act, L.mats[0].q);
     for (int i = 0; i < nmat; ++i) {
         if (nact_host) nact_host[i] = L.mats[(size_t)i].n_act;
         if (transposed_host) transposed_host[i] = L.mats[(size_t)i].transposed;

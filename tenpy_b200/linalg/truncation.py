@@ -107,26 +107,104 @@ def truncate(S, options):
     return mask, norm_new, TruncationError.from_S(S[np.logical_not(mask)])
 
 
-def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'], guess=None, full_out=None):
+subspace_stats = {'tried': 0, 'used': 0, 'residuals': []}   # diagnostics of the subspace warm start
+
+
+def _subspace_svd(theta, subspace, tol, chi_max, qtotal_LR, inner_labels):
+    """SVD of `theta` restricted to the span of the previously kept left (or right) singular vectors.
+
+    With ``P = U_k U_k^dagger`` the part ``(1 - P) theta`` is what a two-site update adds to the old basis; once the
+    state has converged its norm is below the truncation tolerance and ``theta`` can be decomposed inside the old
+    subspace: ``theta ~= U_k svd(U_k^dagger theta)`` -- a (chi x d chi) instead of a (d chi x d chi) problem whose
+    rows are already nearly orthogonal, graded and sorted, and the kept isometry needs no completion.
+    Returns ``None`` (caller falls back to the full SVD) unless ``|(1-P) theta| <= tol |theta|``."""
+    Uk, VHk = subspace
+    chinfo = theta.chinfo
+    qtotal_L, qtotal_R = qtotal_LR
+    if qtotal_L is None and qtotal_R is None:
+        qtotal_R = theta.qtotal
+    if qtotal_L is None:
+        qtotal_L = chinfo.make_valid(theta.qtotal - qtotal_R)
+    elif qtotal_R is None:
+        qtotal_R = chinfo.make_valid(theta.qtotal - qtotal_L)
+    qtotal_L, qtotal_R = chinfo.make_valid(qtotal_L), chinfo.make_valid(qtotal_R)
+    need = min(chi_max if chi_max is not None else min(theta.shape), min(theta.shape))
+    nrm = npc.norm(theta)
+    if Uk is not None and Uk.rank == 2 and need <= Uk.shape[1] < theta.shape[0]:
+        try:
+            Uk.legs[0].test_equal(theta.legs[0])
+        except ValueError:
+            return None
+        subspace_stats['tried'] += 1
+        a2 = npc.tensordot(Uk.conj(), theta, axes=[0, 0])
+        a2.iset_leg_labels([None, theta._labels[1]])
+        back = npc.tensordot(Uk, a2, axes=[1, 0])
+        back.iset_leg_labels(theta.get_leg_labels())
+        rel = npc.norm(theta - back) / nrm
+        subspace_stats['residuals'].append(rel)
+        if rel > tol:
+            return None
+        U2, S, VH = npc.svd(a2, qtotal_LR=[chinfo.make_valid(qtotal_L - Uk.qtotal), qtotal_R],
+                            inner_labels=inner_labels, deflation_tol=tol, n_keep=chi_max)
+        U = npc.tensordot(Uk, U2, axes=[1, 0])
+        U.iset_leg_labels([theta._labels[0], inner_labels[0]])
+        subspace_stats['used'] += 1
+        return U, S, VH, rel * nrm
+    if VHk is not None and VHk.rank == 2 and need <= VHk.shape[0] < theta.shape[1]:
+        try:
+            VHk.legs[1].test_equal(theta.legs[1])
+        except ValueError:
+            return None
+        subspace_stats['tried'] += 1
+        a2 = npc.tensordot(theta, VHk.conj(), axes=[1, 1])
+        a2.iset_leg_labels([theta._labels[0], None])
+        back = npc.tensordot(a2, VHk, axes=[1, 0])
+        back.iset_leg_labels(theta.get_leg_labels())
+        rel = npc.norm(theta - back) / nrm
+        subspace_stats['residuals'].append(rel)
+        if rel > tol:
+            return None
+        U, S, VH2 = npc.svd(a2, qtotal_LR=[qtotal_L, chinfo.make_valid(qtotal_R - VHk.qtotal)],
+                            inner_labels=inner_labels, deflation_tol=tol, n_keep=chi_max)
+        VH = npc.tensordot(VH2, VHk, axes=[1, 0])
+        VH.iset_leg_labels([inner_labels[1], theta._labels[1]])
+        subspace_stats['used'] += 1
+        return U, S, VH, rel * nrm
+    return None
+
+
+def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'], guess=None, full_out=None,
+              subspace=None):
     """SVD of the matrix `theta` and truncation (reference truncation.py:258).
 
     Returns ``(U, S, VH, err, renormalization)`` with ``theta ~= U diag(S * renormalization) VH``.
-    Extensions: `guess` is handed to :func:`npc.svd` (warm start); if `full_out` is a list, the untruncated
-    ``(U, VH)`` are appended to it (shallow copies, to be used as the next guess).  Option
+    Extensions (all optional, the defaults reproduce the reference's behaviour up to the deflation tolerance):
     ``trunc_par['svd_deflation_tol']`` (default 1e-10): singular directions below that fraction of ``|theta|``
     are not iterated to convergence inside the Jacobi SVD -- their values are reported approximately
     (absolute error below the tolerance) and their vectors are an orthonormal completion; the state changes by
-    at most that relative amount, the energy to second order in it.  Without `full_out` only the vectors a
-    truncation can keep (``chi_max``) are completed; with it the bases are completed fully, because the next
-    warm start needs a complete orthonormal basis."""
-    U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR, inner_labels=inner_labels,
-                       guess=guess, deflation_tol=trunc_par.get('svd_deflation_tol', 1.e-10),
-                       n_keep=(trunc_par.get('chi_max', 100) if full_out is None else None))
+    at most that relative amount, the energy to second order in it.
+    `subspace` = ``(U_k, VH_k)``, the truncated isometries kept at this bond by the previous update: see
+    :func:`_subspace_svd` (used only if the part of `theta` outside their span is below the same tolerance; its
+    weight is added to the truncation error).
+    `guess` is handed to :func:`npc.svd` (complete orthonormal bases, warm start); if `full_out` is a list the
+    untruncated ``(U, VH)`` are appended to it."""
+    tol = trunc_par.get('svd_deflation_tol', 1.e-10)
+    chi_max = trunc_par.get('chi_max', 100)
+    res = _subspace_svd(theta, subspace, tol, chi_max, qtotal_LR, inner_labels) if subspace is not None else None
+    lost = 0.
+    if res is not None:
+        U, S, VH, lost = res
+    else:
+        U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR,
+                           inner_labels=inner_labels, guess=guess, deflation_tol=tol,
+                           n_keep=(chi_max if full_out is None else None))
     if full_out is not None:
         full_out.append((U.copy(deep=False), VH.copy(deep=False)))
-    renormalization = np.linalg.norm(S)
+    renormalization = np.sqrt(np.sum(S**2) + lost**2)
     S = S / renormalization
     piv, new_norm, err = truncate(S, trunc_par)
+    if lost:
+        err = err + TruncationError.from_norm(np.sqrt(max(0., 1. - (lost / renormalization)**2)))
     new_len_S = np.sum(piv, dtype=np.int_)
     if new_len_S * 100 < len(S) and (trunc_par.get('chi_max', 100) is None or
                                      new_len_S != trunc_par.get('chi_max', 100)):
