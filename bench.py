@@ -253,7 +253,10 @@ def run_b200(args):
     model = TFIChain({'L': L, 'J': J, 'g': g, 'conserve': None})
     psi = synthetic_mps(model, L, chi, d, seed=rank)
     opts = {'mixer': None, 'combine': True, 'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None},
-            'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N}}
+            'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N},
+            # cold-started SVD at every bond (the subspace warm start would only engage below the 1e-10 tolerance,
+            # the Lanczos update of this workload changes theta by ~2e-7 per bond)
+            'svd_warm_start': False}
     eng = dmrg.TwoSiteDMRGEngine(psi, model, opts)
 
     def barrier():
