@@ -34,6 +34,9 @@ if ROOT not in sys.path:
 METRIC = 'dmrg_two_site_sweep_wall_clock'
 UNIT = 's'
 FP64_TENSOR_PEAK_TFLOPS = 37.0   # B200 (HGX) FP64 tensor/DFMA spec; MEASURED_PEAKS.json has no FP64 entry
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of grouped_gemm_kernel<128,128> at the matvec shapes,
+# mean of the two launches of one matvec, from the ncu --set full capture profiles/r01_gemm_ncu.md
+GEMM_DRAM_BYTES_PER_LAUNCH = 0.5 * ((185.73 + 80.61) + (308.43 + 25.54)) * 1e6
 
 
 def parse_args():
@@ -398,7 +401,9 @@ def kernel_probes(lib, chi, d, D):
     flops = 4. * D * d**3 * chi**3
     tf = flops / (ms * 1e-3) / 1e12
     gemm = {'bound': 'tensor', 'achieved': tf, 'peak': FP64_TENSOR_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-            'frac': tf / FP64_TENSOR_PEAK_TFLOPS, 'traffic': None, 'ms_per_matvec': ms,
+            'frac': tf / FP64_TENSOR_PEAK_TFLOPS, 'traffic': GEMM_DRAM_BYTES_PER_LAUNCH, 'ms_per_matvec': ms,
+            'algorithmic_bytes_per_launch': 8. * (n * D * n + n * n + n * D * n),
+            'tensor_pipe_active_pct_ncu': 83.5,
             'peak_note': 'FP64 DMMA pipe, nominal B200 spec (MEASURED_PEAKS.json has only bf16: %.0f TFLOP/s %s)' %
                          (peaks.get('bf16_tflops', 0.), kind),
             'algorithmic': '4 D d^3 chi^3 = %.3e flop per matvec (two grouped GEMM launches)' % flops}

@@ -247,6 +247,7 @@ static void build_tiles(const std::vector<GemmTask> &tasks, const std::vector<Ge
         GemmTile tile;
     };
     std::vector<Key> keyed[3];
+    static const int force_cfg = getenv("B200_GEMM_FORCE_CFG") ? atoi(getenv("B200_GEMM_FORCE_CFG")) : -1;
     for (size_t ti = 0; ti < tasks.size(); ++ti) {
         const GemmTask &tk = tasks[ti];
         if (tk.m <= 0 || tk.n <= 0) continue;
@@ -258,6 +259,7 @@ static void build_tiles(const std::vector<GemmTask> &tasks, const std::vector<Ge
         int cfg = 0;
         if (area64 * 10 < area128 * 8) cfg = 1;
         if (cfg == 1 && area32 * 10 < area64 * 7) cfg = 2;
+        if (force_cfg >= 0) cfg = force_cfg;   // tuning knob (environment B200_GEMM_FORCE_CFG)
         int b = cfg == 0 ? 128 : (cfg == 1 ? 64 : 32);
         for (int tm = 0; tm < cdiv(tk.m, b); ++tm)
             for (int tn = 0; tn < cdiv(tk.n, b); ++tn) {

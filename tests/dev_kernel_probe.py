@@ -24,6 +24,15 @@ if sys.argv[1] == 'gemm':
         t1 = npc.tensordot(LHeff, theta, axes=[2, 0])
         t2 = npc.tensordot(t1, RHeff, axes=[[1, 2], [0, 1]])
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(10):
+        t1 = npc.tensordot(LHeff, theta, axes=[2, 0])
+        t2 = npc.tensordot(t1, RHeff, axes=[[1, 2], [0, 1]])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 10
+    print('matvec %.3f ms  %.2f TFLOP/s' % (ms, 4 * D * d**3 * chi**3 / ms / 1e9))
 else:
     q, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64, device='cuda'))
     q2, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64, device='cuda'))
