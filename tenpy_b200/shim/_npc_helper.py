@@ -168,6 +168,35 @@ def Array_iscale_prefactor(self, prefactor):
     return self
 
 
+def _svd_worker(a, full_matrices, compute_uv, overwrite_a, cutoff, qtotal_LR, inner_qconj):
+    """host-buffer replacement of npc._svd_worker (npc:4950): the per-block LAPACK loop becomes ONE batched
+    block-Jacobi call (b200_block_svd_f64).  Installed by :func:`install_workers` (plain assignment, the reference
+    looks the worker up by module-global name, npc:3758)."""
+    if full_matrices or a.dtype.kind == 'c':
+        raise NotImplementedError('tenpy_b200 shim: full_matrices / complex SVD')
+    npc = _np_conserved
+    from ..linalg import np_conserved as bnpc
+    da = _to_device_array(a)
+    if not compute_uv:
+        S = bnpc.svd(da, compute_uv=False, cutoff=cutoff)
+        return None, S, None
+    dU, S, dVH = bnpc.svd(da, cutoff=cutoff, qtotal_LR=list(qtotal_LR), inner_qconj=inner_qconj)
+    chinfo = a.chinfo
+    new_leg_R = npc.LegCharge.from_qind(chinfo, dVH.legs[0].slices, dVH.legs[0].charges, dVH.legs[0].qconj)
+    U = npc.Array([a.legs[0], new_leg_R.conj()], a.dtype, dU.qtotal)
+    VH = npc.Array([new_leg_R, a.legs[1]], a.dtype, dVH.qtotal)
+    U._data, U._qdata, U._qdata_sorted = dU.get_blocks_host(), np.array(dU._layout.qdata, dtype=np.intp), True
+    VH._data, VH._qdata, VH._qdata_sorted = dVH.get_blocks_host(), np.array(dVH._layout.qdata, dtype=np.intp), True
+    return U, S, VH
+
+
+def install_workers():
+    """after ``import tenpy``: replace the pure-Python LAPACK workers that are not behind `use_cython`."""
+    import tenpy.linalg.np_conserved as npc
+    npc._svd_worker = _svd_worker
+    return npc
+
+
 # ------------------------------------------------------------------------------------- installation
 #: reference function name -> name exported by this module
 EXPORTS = ['_make_stride', 'ChargeInfo_make_valid', 'ChargeInfo_check_valid', 'LegPipe__init_from_legs',

@@ -37,6 +37,13 @@ res = dmrg.run(psi, M, dict(mixer=True, max_E_err=1e-10, trunc_params=dict(chi_m
                             max_sweeps=8))
 calls = backend.get_lib().calls
 assert calls.get('tdot_plan', 0) > 100 and calls.get('dot', 0) > 10
+# second run with the SVD worker replaced as well (plain assignment, INTEGRATION.md section A)
+shim.install_workers()
+psi2 = MPS.from_product_state(M.lat.mps_sites(), ['up', 'down'] * (L // 2), bc='finite')
+res2 = dmrg.run(psi2, M, dict(mixer=None, max_E_err=1e-10, trunc_params=dict(chi_max=30, svd_min=1e-10), combine=True,
+                              max_sweeps=8))
+assert backend.get_lib().calls.get('block_svd', 0) > 10
+assert abs(res2['E'] - res['E']) < 1e-9, (res2['E'], res['E'])
 print('E=%.12f' % res['E'])
 '''
 
