@@ -256,9 +256,13 @@ static void build_tiles(const std::vector<GemmTask> &tasks, const std::vector<Ge
         int64_t area128 = cdiv(tk.m, 128) * cdiv(tk.n, 128) * 128 * 128;
         int64_t area64 = cdiv(tk.m, 64) * cdiv(tk.n, 64) * 64 * 64;
         int64_t area32 = cdiv(tk.m, 32) * cdiv(tk.n, 32) * 32 * 32;
-        int cfg = 0;
-        if (area64 * 10 < area128 * 8) cfg = 1;
-        if (cfg == 1 && area32 * 10 < area64 * 7) cfg = 2;
+        // 64x64 tiles (4 warps, 4 CTAs/SM) are the default: measured on B200 at the chi=1024 matvec they reach
+        // 31.7 TFLOP/s against 26.8 for 128x128 (8 warps, 1 CTA/SM: fewer resident warps to cover the DMMA
+        // latency, and 768 tiles = 5.19 waves of 148 SMs); see profiles/r01_tile_config.md.  The 128x128 kernel
+        // stays reachable through B200_GEMM_FORCE_CFG=0 for experiments.
+        (void)area128;
+        int cfg = 1;
+        if (area32 * 10 < area64 * 7) cfg = 2;
         if (force_cfg >= 0) cfg = force_cfg;   // tuning knob (environment B200_GEMM_FORCE_CFG)
         int b = cfg == 0 ? 128 : (cfg == 1 ? 64 : 32);
         for (int tm = 0; tm < cdiv(tk.m, b); ++tm)

@@ -249,8 +249,6 @@ class LegCharge:
 
     def test_contractible(self, other):
         """Raise ValueError unless `self` can be contracted with `other` (reference :1071)."""
-        if self is other.__dict__.get('_conj_of', None):
-            return
         if self.chinfo != other.chinfo:
             raise ValueError('incompatible ChargeInfo')
         if self.qconj != -other.qconj:
@@ -398,7 +396,6 @@ class LegCharge:
     def __getstate__(self):
         d = dict(self.__dict__)
         d.pop('_layout_key', None)
-        d.pop('_conj_of', None)
         return d
 
     def __setstate__(self, state):

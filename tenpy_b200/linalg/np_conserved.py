@@ -17,7 +17,6 @@ real.  Reference line numbers ("npc:N") refer to tenpy/linalg/np_conserved.py.
 """
 # Copyright (C) 2026 tenpy_b200 authors. Apache-2.0.
 
-import copy as copy_module
 import itertools
 import warnings
 
@@ -112,7 +111,7 @@ class Array:
         if labels is not None:
             self.iset_leg_labels(labels)
         self._layout = BlockLayout(np.zeros((0, self.rank), np.int64), np.zeros((0, self.rank), np.int64))
-        self._buf = backend.zeros(0) if False else None
+        self._buf = None
         self._qdata_sorted = True
 
     # ------------------------------------------------------------------ basic properties

@@ -40,6 +40,55 @@ class _ChainModel:
             w_charges = [None] * (self.L + 1)
         self.H_MPO = MPO.from_grids(sites, [grid] * self.L, w_charges, IdL, IdR)
         self.lat_sites = sites
+        self._grid, self._IdL, self._IdR = grid, IdL, IdR
+        self._H_bond = None
+
+    @property
+    def H_bond(self):
+        """Nearest-neighbour bond terms, ``H_bond[j]`` acting on sites ``(j-1, j)``, ``H_bond[0] = None``.
+
+        Same decomposition as the reference's `calc_H_bond_from_MPO` (``tenpy/models/model.py:752``): the
+        two-site part is ``sum_b W[IdL, b] (x) W[b, IdR]``; the onsite term ``W[IdL, IdR]`` of a site is shared
+        half-half between its two bonds, fully at the chain ends.  Arrays with labels ``p0, p0*, p1, p1*``."""
+        if self._H_bond is None:
+            from .linalg import np_conserved as npc
+            grid, IdL, IdR, L = self._grid, self._IdL, self._IdR, self.L
+            site = self.sites[0]
+            d = site.dim
+
+            def dense(entry):
+                res = np.zeros((d, d))
+                for coef, name in (entry or []):
+                    res = res + coef * site.get_dense(name)
+                return res
+
+            onsite = dense(grid[IdL][IdR])
+            pair = np.zeros((d, d, d, d))
+            for b in range(len(grid)):
+                if b in (IdL, IdR):
+                    continue
+                pair += np.einsum('ij,kl->ijkl', dense(grid[IdL][b]), dense(grid[b][IdR]))
+            one = np.eye(d)
+            legs = [site.leg, site.leg.conj(), site.leg, site.leg.conj()]
+            H_bond = [None] * L
+            for j in range(1, L):
+                s_i = 1. if j - 1 == 0 else 0.5
+                s_j = 1. if j == L - 1 else 0.5
+                h = pair + s_i * np.einsum('ij,kl->ijkl', onsite, one) + s_j * np.einsum('ij,kl->ijkl', one, onsite)
+                H_bond[j] = npc.Array.from_ndarray(h, legs, labels=['p0', 'p0*', 'p1', 'p1*'], cutoff=1e-16)
+            self._H_bond = H_bond
+        return self._H_bond
+
+    def bond_energies(self, psi):
+        """``<psi| H_bond[j] |psi>`` for ``j = 1 .. L-1`` (reference model.py `NearestNeighborModel.bond_energies`
+        :706); needs `psi` in canonical form around each bond."""
+        from .linalg import np_conserved as npc
+        E = []
+        for j in range(1, self.L):
+            theta = psi.get_theta(j - 1, n=2)
+            Hth = npc.tensordot(self.H_bond[j], theta, axes=(['p0*', 'p1*'], ['p0', 'p1']))
+            E.append(float(npc.inner(theta, Hth, axes='labels', do_conj=True)))
+        return np.array(E)
 
 
 class TFIChain(_ChainModel):

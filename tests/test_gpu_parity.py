@@ -191,6 +191,34 @@ def test_dmrg_tfi_parity(gpu_lib, g_dm):
     _check(res, psi, g_dm, 'tfip', 12)
 
 
+_MID_OPTS = {'mixer': True, 'mixer_params': {'amplitude': 1e-5, 'decay': 2., 'disable_after': 8}, 'max_E_err': 1e-11,
+             'max_S_err': 1e-10, 'combine': True, 'max_sweeps': 40,
+             'lanczos_params': {'P_tol': 1e-22, 'N_max': 40}}
+
+
+def test_dmrg_mid_xxz_sz(gpu_lib):
+    """scaled-down BASELINE.json configs[2]: XXZ L=32, Sz conserved, chi=96 (truncating); golden from the
+    reference (tests/golden/make_golden_mid.py): E = -16.50060013071288"""
+    from tenpy_b200.models import SpinChain
+    g = h.load('dmrg_mid.npz')
+    L = 32
+    M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 1.5, 'conserve': 'Sz'})
+    res, psi = _run(M, ['up', 'down'] * (L // 2), dict(_MID_OPTS, trunc_params={'chi_max': 96, 'svd_min': 1e-10}))
+    assert list(psi.chi) == list(g['xxz32_chi'])
+    _check(res, psi, g, 'xxz32', L)
+
+
+def test_dmrg_mid_hubbard(gpu_lib):
+    """scaled-down BASELINE.json configs[3]: Fermi-Hubbard L=12, (N, Sz) conserved, chi=160; reference
+    E = -6.526243382515468"""
+    from tenpy_b200.models import FermiHubbardChain
+    g = h.load('dmrg_mid.npz')
+    L = 12
+    M = FermiHubbardChain({'L': L, 't': 1., 'U': 4., 'mu': 0.})
+    res, psi = _run(M, ['up', 'down'] * (L // 2), dict(_MID_OPTS, trunc_params={'chi_max': 1000, 'svd_min': 1e-5}))
+    _check(res, psi, g, 'hub12', L)
+
+
 def test_full_size_properties(gpu_lib):
     """BASELINE.json configs[1] shapes (chi=1024, d=2, D=3): size-independent properties of the hot path"""
     import torch
