@@ -34,9 +34,18 @@ if ROOT not in sys.path:
 METRIC = 'dmrg_two_site_sweep_wall_clock'
 UNIT = 's'
 FP64_TENSOR_PEAK_TFLOPS = 37.0   # B200 (HGX) FP64 tensor/DFMA spec; MEASURED_PEAKS.json has no FP64 entry
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of grouped_gemm_kernel<128,128> at the matvec shapes,
-# mean of the two launches of one matvec, from the ncu --set full capture profiles/r01_gemm_ncu.md
-GEMM_DRAM_BYTES_PER_LAUNCH = 0.5 * ((185.73 + 80.61) + (308.43 + 25.54)) * 1e6
+
+
+def gemm_ncu_numbers():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch and tensor-pipe activity of the matvec GEMM kernel,
+    taken from the committed ncu --set full summary (profiles/gemm_ncu.json, written from the capture named in it);
+    ``(None, None, None)`` if no capture of the current kernel configuration is committed."""
+    path = os.path.join(ROOT, 'profiles', 'gemm_ncu.json')
+    if not os.path.exists(path):
+        return None, None, None
+    with open(path) as f:
+        d = json.load(f)
+    return d.get('dram_bytes_per_launch'), d.get('tensor_pipe_active_pct'), d.get('source')
 
 
 def parse_args():
@@ -255,7 +264,8 @@ def run_b200(args):
     g = g0 + 0.02 * rank
     model = TFIChain({'L': L, 'J': J, 'g': g, 'conserve': None})
     psi = synthetic_mps(model, L, chi, d, seed=rank)
-    opts = {'mixer': None, 'combine': True, 'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None},
+    opts = {'mixer': None, 'combine': True, 'diag_method': 'lanczos',      # as tests/benchmark/dmrg_infinite.py:9,44
+            'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None},
             'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N},
             # cold-started SVD at every bond (the subspace warm start would only engage below the 1e-10 tolerance,
             # the Lanczos update of this workload changes theta by ~2e-7 per bond)
@@ -339,7 +349,7 @@ def run_b200(args):
     dominant = max(shares, key=shares.get) if shares else 'gemm'
     roofline = roof['svd'] if dominant == 'svd' else roof['gemm']
     roofline = dict(roofline)
-    roofline['kernel'] = 'jacobi_round_kernel (block SVD)' if dominant == 'svd' else 'grouped_gemm_kernel<128,128> (matvec)'
+    roofline['kernel'] = 'jacobi_round_kernel (block SVD)' if dominant == 'svd' else 'grouped_gemm_kernel<64,64> (matvec)'
     roofline['share_of_step'] = shares.get(dominant)
     if e2e:
         e2e['value'] = float(allst[:, 3].max()) / world
@@ -400,10 +410,11 @@ def kernel_probes(lib, chi, d, D):
     ms = ev0.elapsed_time(ev1) / reps
     flops = 4. * D * d**3 * chi**3
     tf = flops / (ms * 1e-3) / 1e12
+    traffic, pipe_pct, ncu_src = gemm_ncu_numbers()
     gemm = {'bound': 'tensor', 'achieved': tf, 'peak': FP64_TENSOR_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-            'frac': tf / FP64_TENSOR_PEAK_TFLOPS, 'traffic': GEMM_DRAM_BYTES_PER_LAUNCH, 'ms_per_matvec': ms,
+            'frac': tf / FP64_TENSOR_PEAK_TFLOPS, 'traffic': traffic, 'ms_per_matvec': ms,
             'algorithmic_bytes_per_launch': 8. * (n * D * n + n * n + n * D * n),
-            'tensor_pipe_active_pct_ncu': 83.5,
+            'tensor_pipe_active_pct_ncu': pipe_pct, 'ncu_source': ncu_src,
             'peak_note': 'FP64 DMMA pipe, nominal B200 spec (MEASURED_PEAKS.json has only bf16: %.0f TFLOP/s %s)' %
                          (peaks.get('bf16_tflops', 0.), kind),
             'algorithmic': '4 D d^3 chi^3 = %.3e flop per matvec (two grouped GEMM launches)' % flops}

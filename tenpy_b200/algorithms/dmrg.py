@@ -23,7 +23,7 @@ from .mps_common import TwoSiteH, DensityMatrixMixer
 
 logger = logging.getLogger(__name__)
 
-__all__ = ['run', 'TwoSiteDMRGEngine', 'chi_list', 'entropy']
+__all__ = ['run', 'TwoSiteDMRGEngine', 'chi_list', 'entropy', 'full_diag_effH']
 
 
 def entropy(p, n=1):
@@ -60,6 +60,31 @@ def run(psi, model, options):
             'sweep_statistics': engine.sweep_stats}
 
 
+def full_diag_effH(effH, theta_guess, keep_sector=True):
+    """Exact diagonalisation of a small effective Hamiltonian (reference dmrg.py:1176).
+
+    The matrix is contracted with the same device operations as the matvec and diagonalised by the batched
+    Jacobi `eigh` kernel; only the block of the charge sector of `theta_guess` is used."""
+    if not keep_sector:
+        raise NotImplementedError('keep_sector=False')
+    fullH = effH.to_matrix()
+    pipe = theta_guess.make_pipe(effH.acts_on, qconj=+1)
+    fullH.legs[0].test_equal(pipe)
+    qi = pipe.get_qindex_of_charges(theta_guess.qtotal)
+    if not np.any(fullH._qdata[:, 0] == qi):
+        logger.warning('H is zero in the given block, nothing to diagonalize. We just return the initial state.')
+        return 0., theta_guess
+    W, V = npc.eigh(fullH)
+    sl = pipe.get_slice(qi)
+    j = sl.start + int(np.argmin(W[sl]))
+    mask = np.zeros(len(W), dtype=bool)
+    mask[j] = True
+    V.iproject(mask, 1)
+    theta = V.squeeze(1)
+    theta = theta.split_legs([0]).iset_leg_labels(effH.acts_on)
+    return float(W[j]), theta
+
+
 class TwoSiteDMRGEngine:
     """Engine of the two-site DMRG (reference dmrg.py:846 on top of :112 and mps_common.py:60)."""
     EffectiveH = TwoSiteH
@@ -75,16 +100,18 @@ class TwoSiteDMRGEngine:
         self.trunc_params = dict(options.get('trunc_params', {}))
         self.lanczos_params = dict(options.get('lanczos_params', {}))
         self.chi_list = options.get('chi_list', None)
-        self.diag_method = options.get('diag_method', 'lanczos')
-        if self.diag_method not in ('default', 'lanczos'):
+        self.diag_method = options.get('diag_method', 'default')
+        if self.diag_method not in ('default', 'lanczos', 'ED_block'):
             raise NotImplementedError('diag_method ' + repr(self.diag_method))
         self.N_sweeps_check = options.get('N_sweeps_check', 1)
-        self.min_sweeps = options.get('min_sweeps', int(1.5 * self.N_sweeps_check))
-        self.max_sweeps = options.get('max_sweeps', 1000)
-        self.max_E_err = options.get('max_E_err', 1.e-8)
-        self.max_S_err = options.get('max_S_err', 1.e-5)
-        self.max_seconds = 3600 * options.get('max_hours', 24 * 365)
-        self.E_tol_to_trunc = options.get('E_tol_to_trunc', None)
+        default_min_sweeps = int(1.5 * self.N_sweeps_check)
+        if self.chi_list is not None:
+            default_min_sweeps = max(max(self.chi_list.keys()), default_min_sweeps)
+        options.setdefault('min_sweeps', default_min_sweeps)
+        mixer_params = options.setdefault('mixer_params', {})
+        mixer_params.setdefault('amplitude', 1.e-5)       # finite-chain defaults of the reference (dmrg.py:205-212)
+        mixer_params.setdefault('decay', 2.)
+        mixer_params.setdefault('disable_after', 15)
         self.sweeps = options.get('sweep_0', 0)
         self.time0 = time.time()
         self.mixer = None
@@ -103,16 +130,18 @@ class TwoSiteDMRGEngine:
         self.update_LP_RP = (True, False)
         self.E_trunc_list = []
         self.trunc_err_list = []
+        self._meas_E_trunc = False
         self._entropy_approx = [None] * psi.L
         self.reset_stats()
-        self.mixer_activate()
 
     # ------------------------------------------------------------------ statistics
     def reset_stats(self):
+        """Reference dmrg.py:492."""
         self.update_stats = {'i0': [], 'age': [], 'E_total': [], 'N_lanczos': [], 'time': [], 'err': [],
                              'E_trunc': [], 'ov_change': []}
-        self.sweep_stats = {'sweep': [], 'N_updates': [], 'E': [], 'S': [], 'time': [], 'max_trunc_err': [],
-                            'max_E_trunc': [], 'max_chi': [], 'norm_err': []}
+        self.sweep_stats = {'sweep': [], 'N_updates': [], 'E': [], 'Delta_E': [], 'S': [], 'Delta_S': [],
+                            'max_S': [], 'time': [], 'max_trunc_err': [], 'max_E_trunc': [], 'max_chi': [],
+                            'norm_err': []}
         self.shelve = False
         self.time0 = time.time()
 
@@ -124,67 +153,163 @@ class TwoSiteDMRGEngine:
             return
         if Mixer_class is True or Mixer_class == 'DensityMatrixMixer':
             Mixer_class = self.DefaultMixer
-        self.mixer = Mixer_class(self.options.get('mixer_params', {}), self.sweeps)
+        self.mixer = Mixer_class(dict(self.options.get('mixer_params', {})), self.sweeps)
 
     def mixer_deactivate(self):
         self.mixer = None
 
+    def mixer_cleanup(self):
+        """Bring the 2-D bond matrices a mixer sweep leaves back to diagonal form: ``S = U s V``, `U` and `V` are
+        absorbed into the neighbouring tensors and into the stored environments (reference mps_common.py:693)."""
+        psi = self.psi
+        for i in range(1, psi.L):
+            S = psi.get_SL(i)
+            if not isinstance(S, npc.Array):
+                continue
+            U, S, V = npc.svd(S, full_matrices=False, inner_labels=['vR', 'vL'])
+            form_L = psi.form[i - 1][1]
+            form_R = psi.form[i][0]
+            B_L = psi.get_B(i - 1, form=None)
+            B_R = psi.get_B(i, form=None)
+            if form_L == 0.:
+                B_L = npc.tensordot(B_L, U, ['vR', 'vL'])
+            elif form_L == 1.:
+                B_L = npc.tensordot(B_L, V.conj().replace_labels(['vR*', 'vL*'], ['vL', 'vR']), ['vR', 'vL'])
+            else:
+                raise RuntimeError('Array S are only supported in A, B, Th or G form.')
+            if form_R == 0.:
+                B_R = npc.tensordot(V, B_R, ['vR', 'vL'])
+            elif form_R == 1.:
+                B_R = npc.tensordot(U.conj().replace_labels(['vR*', 'vL*'], ['vL', 'vR']), B_R, ['vR', 'vL'])
+            else:
+                raise RuntimeError('Array S are only supported in A, B, Th or G form.')
+            psi.set_B(i - 1, B_L, form=psi.form[i - 1])
+            psi.set_SL(i, S)
+            psi.set_B(i, B_R, form=psi.form[i])
+            if self.env.has_LP(i):
+                LP = self.env.get_LP(i)
+                LP = npc.tensordot(LP, U.conj(), ['vR*', 'vL*'])
+                LP = npc.tensordot(LP, U, ['vR', 'vL'])
+                LP.itranspose(['vR*', 'wR', 'vR'])
+                self.env.set_LP(i, LP, age=self.env.get_LP_age(i))
+            if self.env.has_RP(i - 1):
+                RP = self.env.get_RP(i - 1)
+                RP = npc.tensordot(V.conj(), RP, ['vR*', 'vL*'])
+                RP = npc.tensordot(V, RP, ['vR', 'vL'])
+                RP.itranspose(['vL', 'wL', 'vL*'])
+                self.env.set_RP(i - 1, RP, age=self.env.get_RP_age(i - 1))
+        self._svd_guess = {}
+
     # ------------------------------------------------------------------ the run loop (IterativeSweeps.run, :796)
     def run(self):
-        self.is_first = True
+        self.shelve = False
+        self.mixer_activate()                                 # pre_run_initialize (mps_common.py:819)
         while True:
-            if self.stopping_criterion():
+            if self.stopping_criterion(time.time()):
                 break
             self.run_iteration()
         self.post_run_cleanup()
-        return self.sweep_stats['E'][-1] if len(self.sweep_stats['E']) else None, self.psi
+        max_trunc = self.options.get('max_trunc_err', 1.e-4)
+        if max_trunc is not None and len(self.trunc_err_list) and np.max(self.trunc_err_list) > max_trunc:
+            raise ValueError('Maximum truncation error (``max_trunc_err``) exceeded.')   # consistency_check (:810)
+        return self.sweep_stats['E'][-1] if len(self.sweep_stats['E']) else np.nan, self.psi
 
-    def stopping_criterion(self):
-        """Reference dmrg.py:376 `is_converged` + mps_common.py:869."""
-        if self.sweeps >= self.max_sweeps:
+    def stopping_criterion(self, iteration_start_time):
+        """Reference mps_common.py:869 (including its ``>`` comparisons: ``max_sweeps + 1`` sweeps are done when
+        the run does not converge, and a converged run with an active mixer switches the mixer off and goes on)."""
+        min_sweeps = self.options.get('min_sweeps', 1)
+        max_sweeps = self.options.get('max_sweeps', 1000)
+        max_seconds = 3600 * self.options.get('max_hours', 24 * 365)
+        if self.sweeps > max_sweeps:
             return True
-        if time.time() - self.time0 > self.max_seconds:
+        if self.sweeps > min_sweeps and self.is_converged():
+            if self.mixer is None:
+                return True
+            self.mixer_deactivate()
+            return False
+        if iteration_start_time - self.time0 > max_seconds:
             self.shelve = True
             return True
-        if self.sweeps < self.min_sweeps or len(self.sweep_stats['E']) < 2:
-            return False
-        if self.mixer is not None:
-            return False
-        if any(isinstance(s, npc.Array) for s in self.psi._S):
-            # a sweep with the mixer leaves 2-D bond matrices; one mixer-free sweep restores the diagonal form
-            # (the reference does this with Sweep.mixer_cleanup, mps_common.py:693)
-            return False
-        E = self.sweep_stats['E']
-        S = self.sweep_stats['S']
-        Delta_E = (E[-1] - E[-2]) / self.N_sweeps_check
-        Delta_S = (S[-1] - S[-2]) / self.N_sweeps_check
-        return abs(Delta_E / max(abs(E[-1]), 1.)) < self.max_E_err and abs(Delta_S) < self.max_S_err
+        return False
+
+    def is_converged(self):
+        """Reference dmrg.py:376, verbatim criterion ``|Delta_E / max(E, 1)| < max_E_err and |Delta_S| < max_S_err``
+        (note ``max(E, 1)``, not ``max(|E|, 1)``: for negative energies the energy criterion is absolute)."""
+        max_E_err = self.options.get('max_E_err', 1.e-8)
+        max_S_err = self.options.get('max_S_err', 1.e-5)
+        E = self.sweep_stats['E'][-1]
+        Delta_E = self.sweep_stats['Delta_E'][-1]
+        Delta_S = self.sweep_stats['Delta_S'][-1]
+        return abs(Delta_E / max(E, 1.)) < max_E_err and abs(Delta_S) < max_S_err
 
     def run_iteration(self):
-        """Reference dmrg.py:219."""
-        max_trunc_err = 0.
-        max_E_trunc = 0.
-        for _ in range(self.N_sweeps_check):
-            max_trunc_err = max(max_trunc_err, self.sweep())
-            if len(self.E_trunc_list):
-                max_E_trunc = max(max_E_trunc, np.max(np.abs(self.E_trunc_list)))
+        """`N_sweeps_check` sweeps, adaptive Lanczos tolerances, statistics (reference dmrg.py:219-348)."""
+        options = self.options
+        p_tol_to_trunc = options.get('P_tol_to_trunc', 0.05)
+        if p_tol_to_trunc is not None:
+            svd_min = self.trunc_params.get('svd_min', 0.) or 0.
+            trunc_cut = self.trunc_params.get('trunc_cut', 0.) or 0.
+            p_tol_min = max(1.e-30, svd_min**2 * p_tol_to_trunc, trunc_cut**2 * p_tol_to_trunc)
+            p_tol_min = options.get('P_tol_min', p_tol_min)
+            p_tol_max = options.get('P_tol_max', 1.e-4)
+        e_tol_to_trunc = options.get('E_tol_to_trunc', None)
+        if e_tol_to_trunc is not None:
+            e_tol_min = options.get('E_tol_min', 5.e-16)
+            e_tol_max = options.get('E_tol_max', 1.e-4)
+        if len(self.sweep_stats['E']) < 1:
+            E_old = np.nan
+            S_old = np.mean(self.psi.entanglement_entropy())
+        else:
+            E_old = self.sweep_stats['E'][-1]
+            S_old = self.sweep_stats['S'][-1]
+        for _ in range(self.N_sweeps_check - 1):
+            self.sweep(meas_E_trunc=False)
+        max_trunc_err = self.sweep(meas_E_trunc=True)
+        max_E_trunc = np.max(self.E_trunc_list)
+        if p_tol_to_trunc is not None and max_trunc_err > p_tol_min:
+            self.lanczos_params['P_tol'] = max(p_tol_min, min(p_tol_max, max_trunc_err * p_tol_to_trunc))
+        if e_tol_to_trunc is not None and max_E_trunc > e_tol_min:
+            self.lanczos_params['E_tol'] = max(e_tol_min, min(e_tol_max, max_E_trunc * e_tol_to_trunc))
+        entropy_bonds = self._entropy_approx[1:]
+        max_S = max(entropy_bonds)
+        S = np.mean(entropy_bonds)
         E = self.update_stats['E_total'][-1]
-        S_all = [s for s in self._entropy_approx if s is not None]
-        S = max(S_all) if S_all else 0.
+        norm_err = np.linalg.norm(self.psi.norm_test())
         self.sweep_stats['sweep'].append(self.sweeps)
         self.sweep_stats['N_updates'].append(len(self.update_stats['i0']))
         self.sweep_stats['E'].append(E)
+        self.sweep_stats['Delta_E'].append((E - E_old) / self.N_sweeps_check)
         self.sweep_stats['S'].append(S)
+        self.sweep_stats['Delta_S'].append((S - S_old) / self.N_sweeps_check)
+        self.sweep_stats['max_S'].append(max_S)
         self.sweep_stats['time'].append(time.time() - self.time0)
         self.sweep_stats['max_trunc_err'].append(max_trunc_err)
         self.sweep_stats['max_E_trunc'].append(max_E_trunc)
         self.sweep_stats['max_chi'].append(int(np.max(self.psi.chi)))
+        self.sweep_stats['norm_err'].append(norm_err)
         logger.info('sweep %d: E=%.13f S=%.6f chi=%d trunc=%.2e t=%.1fs', self.sweeps, E, S,
                     self.sweep_stats['max_chi'][-1], max_trunc_err, self.sweep_stats['time'][-1])
         return E, self.psi
 
     def post_run_cleanup(self):
-        pass
+        """Reference dmrg.py:402: `mixer_cleanup`, then `_canonicalize` (:455) -- when the final state violates the
+        canonical form by more than ``norm_tol_final`` (a truncating run that is not fully converged), it is
+        re-canonicalised with `MPS.canonical_form`, which also refreshes all Schmidt values."""
+        self.mixer_cleanup()
+        if self.mixer is not None:
+            return
+        norm_tol = self.options.get('norm_tol', 1.e-5)
+        norm_tol_final = self.options.get('norm_tol_final', 1.e-10)
+        norm_err = np.linalg.norm(self.psi.norm_test())
+        if norm_tol is None or (norm_err < norm_tol and norm_err < norm_tol_final):
+            return
+        if norm_err > norm_tol:
+            logger.warning('final DMRG state not in canonical form up to norm_tol=%.2e: norm_err=%.2e', norm_tol,
+                           norm_err)
+        if norm_err > norm_tol_final:
+            self.psi.canonical_form()
+            self.env.clear()
+            self._svd_guess = {}
 
     # ------------------------------------------------------------------ one sweep (mps_common.py:345)
     def get_sweep_schedule(self):
@@ -195,7 +320,9 @@ class TwoSiteDMRGEngine:
         update_LP_RP = [[True, False]] * (L - n) + [[False, True]] * (L - n)
         return zip(i0s, move_right, update_LP_RP)
 
-    def sweep(self, optimize=True):
+    def sweep(self, optimize=True, meas_E_trunc=False):
+        """One sweep right and back left (reference mps_common.py:345, dmrg.py:520)."""
+        self._meas_E_trunc = meas_E_trunc
         self.E_trunc_list = []
         self.trunc_err_list = []
         if optimize and self.chi_list is not None:
@@ -242,8 +369,14 @@ class TwoSiteDMRGEngine:
         return {'E0': E0, 'err': err, 'N': N, 'age': age, 'U': U, 'VH': VH, 'ov_change': ov_change}
 
     def diag(self, theta_guess):
-        """Reference dmrg.py:672 (Lanczos only; the reference's small-N ED shortcut is a host LAPACK call)."""
-        E, theta, N = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params).run()
+        """Reference dmrg.py:672: Lanczos, or for ``diag_method='default'`` and tiny effective Hamiltonians
+        (``N < max_N_for_ED``) the exact diagonalisation of the charge block (`full_diag_effH`)."""
+        N = -1
+        if self.diag_method == 'ED_block' or (self.diag_method == 'default' and
+                                              self.eff_H.N < self.options.get('max_N_for_ED', 400)):
+            E, theta = full_diag_effH(self.eff_H, theta_guess, keep_sector=True)
+        else:
+            E, theta, N = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params).run()
         ov_change = 1. - abs(npc.inner(theta_guess, theta, 'labels', do_conj=True))
         return E, theta, N, ov_change
 
@@ -289,8 +422,11 @@ class TwoSiteDMRGEngine:
         self.psi.set_SR(i0, S)
 
     def update_env(self, **update_data):
-        """Reference mps_common.py:569."""
+        """Reference mps_common.py:569: the parts across the updated bond are dropped, the one needed next is
+        recomputed from `LHeff` / `RHeff` (TwoSiteH.update_LP / update_RP)."""
         i0 = self.i0
+        self.env.del_LP(i0 + 1)
+        self.env.del_RP(i0)
         update_LP, update_RP = self.update_LP_RP
         if update_LP:
             self.eff_H.update_LP(self.env, i0 + 1, update_data['U'])
@@ -301,7 +437,13 @@ class TwoSiteDMRGEngine:
         """Reference dmrg.py:575."""
         i0 = self.i0
         E_trunc = None
+        if self._meas_E_trunc or E0 is None:
+            E_trunc = float(self.env.full_contraction(i0))    # uses the updated LP / RP
+            if E0 is None:
+                E0 = E_trunc
+            E_trunc = E_trunc - E0
         self.trunc_err_list.append(err.eps)
+        self.E_trunc_list.append(E_trunc)
         self.update_stats['i0'].append(i0)
         self.update_stats['age'].append(age)
         self.update_stats['E_total'].append(E0)
@@ -315,10 +457,8 @@ class TwoSiteDMRGEngine:
         """Reference mps_common.py:614: parts that will be recomputed before their next use are dropped."""
         i0 = self.i0
         update_LP, update_RP = self.update_LP_RP
-        if update_LP and not update_RP:
-            # moving right: RP[i0] is outdated (site i0+1 changed)
-            if i0 < self.psi.L - 1:
-                self.env.del_RP(i0)
-        if update_RP and not update_LP:
-            if i0 + 1 > 0:
-                self.env.del_LP(i0 + 1)
+        if update_RP:
+            self.env.del_LP(i0)                               # will update (i0-1, i0) next: LP[i0] is useless
+        if update_LP:
+            self.env.del_RP(i0 + 1)                           # will update (i0+1, i0+2) next: RP[i0+1] is useless
+        self.eff_H = None

@@ -799,6 +799,31 @@ class Array:
         res._layout = BlockLayout(qd, sh)
         return res
 
+    def squeeze(self, axes=None):
+        """Remove legs of length 1; their charge goes into `qtotal` (reference npc:1817).  Metadata only: the
+        packed blocks keep their order and offsets (a unit axis does not change the row-major data)."""
+        if axes is None:
+            axes = [a for a in range(self.rank) if self.shape[a] == 1]
+        else:
+            axes = self.get_leg_indices(axes if isinstance(axes, (list, tuple)) else [axes])
+        for a in axes:
+            if self.shape[a] != 1:
+                raise ValueError('Tried to squeeze non-unit leg')
+        keep = [a for a in range(self.rank) if a not in axes]
+        if len(keep) == 0:
+            raise NotImplementedError('squeeze to a scalar: use to_ndarray()')
+        res = self.copy(deep=False)
+        res.legs = [self.legs[a] for a in keep]
+        res._labels = [self._labels[a] for a in keep]
+        res._set_shape()
+        qtotal = self.qtotal.copy()
+        for a in axes:
+            qtotal = qtotal - self.legs[a].get_charge(0)
+        res.qtotal = self.chinfo.make_valid(qtotal)
+        lay = self._layout
+        res._layout = BlockLayout(np.ascontiguousarray(lay.qdata[:, keep]), np.ascontiguousarray(lay.shapes[:, keep]))
+        return res
+
     def __repr__(self):
         return '<npc.Array shape={0!s} labels={1!s} blocks={2:d}>'.format(self.shape, self._labels,
                                                                          self.stored_blocks)

@@ -150,6 +150,12 @@ class MPOEnvironment:
                 self.set_RP(j - 1, RP, age)
         return RP
 
+    def has_LP(self, i):
+        return self._LP[i] is not None
+
+    def has_RP(self, i):
+        return self._RP[i] is not None
+
     def get_LP_age(self, i):
         return self._LP_age[i]
 
@@ -215,15 +221,25 @@ class MPOEnvironment:
         return RHeff.combine_legs([[p, 'vL*'], [ps, 'vL']], pipes=[pipe, pipe.conj()], new_axes=[2, 1])
 
     def full_contraction(self, i0):
-        """``<bra|H|ket>`` contracted at the bond right of site `i0` (reference mpo.py:3065)"""
-        LP = self.get_LP(i0 + 1, store=False) if i0 + 1 < self.L else None
-        if LP is None:
+        """``<bra|H|ket>`` contracted at the bond right of site `i0` (reference mpo.py:3064 on top of
+        `MPSEnvironment._full_contraction_LP_RP`, mps.py:6706): ``LP[i0+1]`` and ``RP[i0]`` with the bond matrix
+        (1-D Schmidt values, or the 2-D matrix a mixer leaves) of bra and ket in between."""
+        if i0 + 1 == self.L:
             LP = self._contract_LP(i0, self.get_LP(i0, store=False))
-            RP = self.init_RP(self.L - 1)
-            return npc.inner(LP, RP, axes=[['vR*', 'wR', 'vR'], ['vL*', 'wL', 'vL']], do_conj=False)
-        S = self.ket.get_SR(i0)
+        else:
+            LP = self.get_LP(i0 + 1, store=False)
+        S_bra = self.bra.get_SR(i0)
+        if isinstance(S_bra, npc.Array):
+            LP = npc.tensordot(S_bra.conj(), LP, axes=['vL*', 'vR*'])
+        else:
+            LP = LP.scale_axis(S_bra, 'vR*')
+        S_ket = self.ket.get_SR(i0)
+        if isinstance(S_ket, npc.Array):
+            LP = npc.tensordot(LP, S_ket, axes=['vR', 'vL'])
+        else:
+            LP = LP.scale_axis(S_ket, 'vR')
         RP = self.get_RP(i0, store=False)
-        if isinstance(S, npc.Array):
-            raise NotImplementedError('full_contraction across a bond holding a 2-D mixer matrix')
-        LP = LP.scale_axis(S, 'vR').iscale_axis(S, 'vR*')
-        return npc.inner(LP, RP, axes=[['vR*', 'wR', 'vR'], ['vL*', 'wL', 'vL']], do_conj=False)
+        res = npc.inner(LP, RP, axes=[['vR*', 'wR', 'vR'], ['vL*', 'wL', 'vL']], do_conj=False)
+        if self.H.explicit_plus_hc:
+            res = res + np.conj(res)
+        return res

@@ -156,8 +156,8 @@ class MPS:
                 res.append(float(np.log(np.sum(s**(2 * n))) / (1. - n)))
         return np.array(res)
 
-    def norm_test(self):
-        """max deviation of every site tensor from its canonical (isometry) condition."""
+    def isometry_test(self):
+        """max deviation of every site tensor from the isometry condition of its canonical form."""
         out = []
         for i in range(self.L):
             f = self.form[i]
@@ -172,3 +172,77 @@ class MPS:
             d = M.to_ndarray()
             out.append(float(np.max(np.abs(d - np.eye(d.shape[0])))))
         return np.array(out)
+
+    def norm_test(self):
+        """Canonical-form check of the reference (mps.py:4444): for each site the norm differences between the
+        reduced density matrices of ``theta[i]`` and ``S[i]^2`` (left, column 0) / ``S[i+1]^2`` (right, column 1)."""
+        err = np.empty((self.L, 2), dtype=float)
+        for i in range(self.L):
+            th = self.get_theta(i, 1)
+            rho_L = npc.tensordot(th, th.conj(), axes=(['p0', 'vR'], ['p0*', 'vR*']))
+            S = self.get_SL(i)
+            if isinstance(S, npc.Array):
+                rho_L2 = npc.tensordot(S, S.conj(), axes=['vR', 'vR*'])
+            else:
+                rho_L2 = npc.diag(S**2, rho_L.get_leg('vL'), labels=['vL', 'vL*'])
+            err[i, 0] = npc.norm(rho_L - rho_L2)
+            rho_R = npc.tensordot(th, th.conj(), axes=(['vL', 'p0'], ['vL*', 'p0*']))
+            S = self.get_SR(i)
+            if isinstance(S, npc.Array):
+                rho_R2 = npc.tensordot(S, S.conj(), axes=['vL', 'vL*'])
+            else:
+                rho_R2 = npc.diag(S**2, rho_R.get_leg('vR'), labels=['vR', 'vR*'])
+            err[i, 1] = npc.norm(rho_R - rho_R2)
+        return err
+
+    def canonical_form(self, renormalize=True, cutoff=0.):
+        """Bring the finite MPS into right-canonical ``'B'`` form, in place (reference mps.py:4501
+        `canonical_form_finite`): one sweep to the right orthonormalising, one sweep to the left computing all
+        Schmidt values by SVDs.  The reference uses QR in the first sweep; here both sweeps use the batched
+        block-Jacobi SVD (``Q = U``, ``R = S V``), which gives the same canonical form."""
+        L = self.L
+        assert L > 1
+        self.set_SL(0, np.array([1.]))
+        self.set_SR(L - 1, np.array([1.]))
+        if any(f is None for f in self.form):
+            M = self.get_B(0, form=None)
+            form = None
+        else:
+            M = self.get_B(0, form='Th')
+            form = 'B'
+        M = self._normalize_array(M.copy(deep=True), renormalize)
+        R = None
+        for i in range(L - 1):
+            if i > 0:
+                M = npc.tensordot(R, self.get_B(i, form), axes=['vR', 'vL'])
+                M = self._normalize_array(M, renormalize)
+            Mc = M.combine_legs(['vL', 'p'])
+            Q, s, V = npc.svd(Mc, cutoff=0., qtotal_LR=[None, Mc.qtotal], inner_labels=['vR', 'vL'])
+            R = V.iscale_axis(s, 'vL')
+            self.set_B(i, Q.split_legs(0), form='A')
+        M = npc.tensordot(R, self.get_B(L - 1, form), axes=['vR', 'vL'])
+        M = self._normalize_array(M, renormalize)
+        U, S, V = npc.svd(M.combine_legs(['p', 'vR'], qconj=-1), cutoff=cutoff, inner_labels=['vR', 'vL'])
+        if not renormalize:
+            self.norm = self.norm * np.linalg.norm(S)
+        S = S / np.linalg.norm(S)
+        self.set_SL(L - 1, S)
+        self.set_B(L - 1, V.split_legs(1), form='B')
+        for i in range(L - 2, -1, -1):
+            M = self.get_B(i, 'A')
+            M = npc.tensordot(M, U.scale_axis(S, 'vR'), axes=['vR', 'vL'])
+            U, S, V = npc.svd(M.combine_legs(['p', 'vR'], qconj=-1), cutoff=cutoff, qtotal_LR=[None, M.qtotal],
+                              inner_labels=['vR', 'vL'])
+            S = S / np.linalg.norm(S)
+            self.set_SL(i, S)
+            self.set_B(i, V.split_legs(1), form='B')
+        assert len(S) == 1
+        self._B[0] *= float(U.to_ndarray()[0, 0])             # a sign, kept like the reference does
+
+    def _normalize_array(self, arr, renormalize):
+        """Reference mps.py:6151."""
+        nrm = npc.norm(arr)
+        if not renormalize:
+            self.norm = self.norm * nrm
+        arr /= nrm
+        return arr

@@ -145,7 +145,7 @@ def _check(res, psi, g, key, L):
         ref = np.sort(g[key + '_sv_mid'])[::-1]
         k = min(len(sv), len(ref))
         assert np.max(np.abs(sv[:k] - ref[:k])) < 1e-8                          # singular values: 1e-8
-    assert np.nanmax(psi.norm_test()) < 1e-11
+    assert np.nanmax(psi.isometry_test()) < 1e-11
 
 
 def test_dmrg_config1_tfi(gpu_lib, g_dm):

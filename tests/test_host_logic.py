@@ -169,7 +169,7 @@ def test_dmrg_driver_tfi(fake_device):
                                          'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
     assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
     assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
-    assert np.max(psi.norm_test()) < 1e-12
+    assert np.max(psi.isometry_test()) < 1e-12
 
 
 def test_dmrg_driver_charges_and_mixer(fake_device):

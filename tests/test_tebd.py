@@ -47,7 +47,7 @@ def _run_all(names, tol=1e-9):
         assert np.max(np.abs(eng._U[0][L // 2].to_ndarray() - g[name + '_U_half_mid'])) < 1e-14
         eng.update_imag(30)
         _compare(name + '_imag', g, M, psi, eng, tol)
-        assert np.nanmax(psi.norm_test()) < 1e-11               # the sweeps keep the canonical form
+        assert np.nanmax(psi.isometry_test()) < 1e-11               # the sweeps keep the canonical form
         for order in (1, 2, 4):
             psi = MPS.from_product_state(M.lat_sites, state)
             eng = TEBDEngine(psi, M, {'trunc_params': {'chi_max': 32, 'svd_min': 1e-8}})
