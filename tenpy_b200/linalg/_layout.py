@@ -48,22 +48,50 @@ def _contig_strides(shapes):
     return st
 
 
+_INTERN = {}
+_INTERN_MAX = 50000
+
+
 class BlockLayout:
-    """Immutable block table of a packed buffer (see module doc-string)."""
+    """Immutable block table of a packed buffer (see module doc-string).
+
+    Layouts are *interned*: constructing a layout with a block table (``qdata``, ``shapes``) that was seen
+    before returns the very same object.  All caches hanging off a layout (transpose / combine / split /
+    scale records in ``layout.cache``, the contraction plans of ``np_conserved.tensordot`` keyed on layout
+    identity) therefore hit whenever the block *structure* repeats -- every Lanczos iteration of a bond and
+    the same bond in the next sweep -- and the integer bookkeeping that the reference redoes per call
+    (`_tensordot_pre_sort`, pyx:1337; `_tensordot_match_charges`, pyx:1382) is done once per structure.
+    A cache entry that also depends on leg data not visible in the block table (pipes) has to carry
+    ``LegCharge.content_key()`` of those legs in its key.
+    """
     __slots__ = ('qdata', 'shapes', 'sizes', 'offsets', 'size', 'uid', 'rank', 'nblocks', 'cache')
 
-    def __init__(self, qdata, shapes):
+    def __new__(cls, qdata, shapes):
         qdata = np.ascontiguousarray(qdata, dtype=np.int64)
         shapes = np.ascontiguousarray(shapes, dtype=np.int64)
         if qdata.ndim != 2 or qdata.shape != shapes.shape:
             raise ValueError('qdata/shapes mismatch')
-        self.qdata = qdata
-        self.shapes = shapes
+        key = (qdata.shape, qdata.tobytes(), shapes.tobytes())
+        self = _INTERN.get(key)
+        if self is not None:
+            return self
+        self = object.__new__(cls)
+        self.qdata = qdata = qdata.copy()     # private, read-only copies: the table is shared between Arrays
+        self.shapes = shapes = shapes.copy()
+        qdata.flags.writeable = False
+        shapes.flags.writeable = False
         self.nblocks, self.rank = qdata.shape
         self.sizes = np.prod(shapes, axis=1, dtype=np.int64) if self.rank else np.ones(self.nblocks, np.int64)
         self.offsets, self.size = _aligned_offsets(self.sizes)
         self.uid = next(_uid)
         self.cache = {}
+        if len(_INTERN) >= _INTERN_MAX:
+            _INTERN.clear()     # old layouts stay valid (Arrays hold them), they are just no longer canonical
+        _INTERN[key] = self
+        return self
+
+    def __reduce__(self):
+        return (BlockLayout, (np.array(self.qdata), np.array(self.shapes)))
 
     @classmethod
     def from_legs(cls, legs, qdata, presorted=False):

@@ -156,6 +156,18 @@ class LegCharge:
         res._layout_key = None
         return res
 
+    def content_key(self):
+        """Hashable value identifying the charge data of this leg (slices, charges, mod, qconj; for pipes also
+        the incoming legs and `q_map`).  Used in the keys of the index-plan caches hanging off interned
+        :class:`~tenpy_b200.linalg._layout.BlockLayout` objects; the qconj-independent part is cached."""
+        base = self._layout_key
+        if base is None:
+            base = self._layout_key = self._content_base()
+        return (self.qconj, base)
+
+    def _content_base(self):
+        return (self.slices.tobytes(), self.charges.tobytes(), self.chinfo.mod.tobytes())
+
     # --- alternative constructors (reference charges.py:758-841)
     @classmethod
     def from_trivial(cls, ind_len, chargeinfo=None, qconj=1):
@@ -210,6 +222,7 @@ class LegCharge:
         """Shallow copy with opposite ``qconj`` (reference charges.py:979)."""
         res = self.copy()
         res.qconj = -self.qconj
+        res._layout_key = self._layout_key      # same arrays: the qconj-independent part of the key carries over
         return res
 
     def flip_charges_qconj(self):
@@ -428,6 +441,11 @@ class LegPipe(LegCharge):
         res.__dict__.update(self.__dict__)
         res._layout_key = None
         return res
+
+    def _content_base(self):
+        # incoming legs enter with their qconj *relative* to the pipe's: invariant under conj(), which flips both
+        return (LegCharge._content_base(self), self.q_map.tobytes(),
+                tuple((l.qconj * self.qconj, l.content_key()[1]) for l in self.legs))
 
     def to_LegCharge(self):
         """Forget the incoming legs."""

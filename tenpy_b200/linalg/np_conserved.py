@@ -574,7 +574,7 @@ class Array:
         lay = self._layout
         if lay.nblocks == 0:
             return self
-        key = ('S', axis, id(self.legs[axis].slices))
+        key = ('S', axis, self.legs[axis].slices.tobytes())
         cached = lay.cache.get(key)
         if cached is None:
             rec = plan_scale_axis(lay, self.legs[axis], axis)
@@ -695,7 +695,7 @@ class Array:
         lay = self._layout
         if lay.nblocks == 0:
             return res
-        key = ('C', tuple(tuple(cl) for cl in combine_legs), tuple(new_axes), tuple(id(p.q_map) for p in pipes))
+        key = ('C', tuple(tuple(cl) for cl in combine_legs), tuple(new_axes), tuple(p.content_key() for p in pipes))
         cached = lay.cache.get(key)
         if cached is None:
             new_layout, rec = plan_combine(lay, self.legs, combine_legs, new_axes, pipes, res_legs)
@@ -739,7 +739,7 @@ class Array:
         lay = self._layout
         if lay.nblocks == 0:
             return res
-        key = ('P', tuple(axes))
+        key = ('P', tuple(axes), tuple(self.legs[a].content_key() for a in axes))
         cached = lay.cache.get(key)
         if cached is None:
             new_layout, rec = plan_split(lay, self.legs, axes, res_legs)
