@@ -112,38 +112,50 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------ CPU (oracle) arm
 def cpu_bond_sample(chi, d, D, lanczos_N, n_bonds, seed=0):
-    """time `n_bonds` two-site updates at the chain centre (full chi) with the dense CPU oracle."""
+    """time `n_bonds` two-site updates at the chain centre (full chi) with the dense CPU oracle, once with the
+    reference's default matvec (combine=True: LHeff.theta.RHeff) and once with its combine=False contraction order
+    inside Lanczos (d times fewer flops); the faster one is the CPU baseline."""
     from oracle import dmrg_dense as od
     rng = np.random.default_rng(seed)
     n = chi * d
-    LHeff = rng.standard_normal((n, D, n))
-    LHeff = LHeff + LHeff.transpose(2, 1, 0)
-    RHeff = rng.standard_normal((D, n, n))
-    RHeff = RHeff + RHeff.transpose(0, 2, 1)
+    LP = rng.standard_normal((chi, D, chi))
+    LP = LP + LP.transpose(2, 1, 0)
+    RP = rng.standard_normal((chi, D, chi))
+    RP = RP + RP.transpose(2, 1, 0)
+    W = od.tfi_mpo(1., 1.)
+    LHeff, RHeff = od.contract_LHeff(LP, W), od.contract_RHeff(RP, W)
     theta = rng.standard_normal((n, n))
     theta /= np.linalg.norm(theta)
     trunc = dict(chi_max=chi, svd_min=1e-45, trunc_cut=None)
     lan = dict(N_min=lanczos_N, N_max=lanczos_N)
-    t0 = time.perf_counter()
-    tm = 0.
-    for b in range(n_bonds):
+
+    def mv_split(x):
+        return od.matvec_split(LP, W, W, RP, x.reshape(chi, d, d, chi)).reshape(n, n)
+    t_mv = {}
+    for name, fn in (('combined', lambda x: od.matvec(LHeff, RHeff, x)), ('split', mv_split)):
+        fn(theta)
         t1 = time.perf_counter()
-        od.matvec(LHeff, RHeff, theta)
-        tm += time.perf_counter() - t1
-        E0, U, S, VH, env, N = od.bond_update(LHeff, RHeff, theta, trunc, lan, move_right=(b % 2 == 0))
-    dt = time.perf_counter() - t0 - tm
-    return dt / n_bonds, tm / n_bonds
+        fn(theta)
+        t_mv[name] = time.perf_counter() - t1
+    best = min(t_mv, key=t_mv.get)
+    t0 = time.perf_counter()
+    for b in range(n_bonds):
+        od.bond_update(LHeff, RHeff, theta, trunc, lan, move_right=(b % 2 == 0),
+                       matvec_fn=mv_split if best == 'split' else None)
+    dt = time.perf_counter() - t0
+    return dt / n_bonds, t_mv, best
 
 
 def cpu_sweep_estimate(args, n_bonds):
     """CPU sweep estimate = (number of full-chi bond updates per sweep) x (time of one such update)."""
     d, D = 2, 3
     full = n_full_bonds(args.L, args.chi, d)
-    per_bond, t_matvec = cpu_bond_sample(args.chi, d, D, args.lanczos_N, n_bonds)
+    per_bond, t_mv, best = cpu_bond_sample(args.chi, d, D, args.lanczos_N, n_bonds)
     from oracle import dmrg_dense as od
     fl = od.matvec_flops(args.chi * d, D, args.chi * d)
-    return {'sweep_s': full * per_bond, 'per_bond_s': per_bond, 'matvec_s': t_matvec,
-            'matvec_gflops': fl / t_matvec / 1e9, 'full_chi_bonds': full}
+    return {'sweep_s': full * per_bond, 'per_bond_s': per_bond, 'matvec_s': t_mv['combined'],
+            'matvec_split_s': t_mv['split'], 'matvec_order_used': best,
+            'matvec_gflops': fl / t_mv['combined'] / 1e9, 'full_chi_bonds': full}
 
 
 def n_full_bonds(L, chi, d):
@@ -164,14 +176,16 @@ def run_reference(args):
         if it >= args.warmup:
             vals.append(est)
     v = float(np.mean([e['sweep_s'] for e in vals]))
-    sample = ('1 bond update at full chi per step (oracle/dmrg_dense.py: %d Lanczos matvecs + gesdd + env update), '
-              'x %d full-chi bonds of the sweep' % (args.lanczos_N, vals[0]['full_chi_bonds']))
+    sample = ('1 bond update at full chi per step (oracle/dmrg_dense.py: %d Lanczos matvecs in the faster of the '
+              "reference's two contraction orders [%s] + gesdd + env update), x %d full-chi bonds of the sweep" %
+              (args.lanczos_N, vals[0]['matvec_order_used'], vals[0]['full_chi_bonds']))
     line = {'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': v * 1e3, 'higher_is_better': False, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
             'config': workload_config(args, 1),
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
-                             'matvec_gflops': float(np.mean([e['matvec_gflops'] for e in vals]))},
+                             'matvec_gflops': float(np.mean([e['matvec_gflops'] for e in vals])),
+                             'matvec_s': vals[0]['matvec_s'], 'matvec_split_s': vals[0]['matvec_split_s']},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -182,6 +196,8 @@ def workload_config(args, n):
                         'path), d=2, MPO D=3, Lanczos N_min=N_max=%d, svd_min=1e-45' %
                         (args.L, 2 * (args.L - 2), args.chi, args.lanczos_N),
             'L': args.L, 'chi': args.chi, 'lanczos_N': args.lanczos_N,
+            'matvec_order': "auto ('split' for theta blocks >= 2^20 elements: LP, W0 W1, RP applied to the split theta, "
+                            "4 D d^2 chi^3 flop instead of the reference default's 4 D d^3 chi^3; same result)",
             'parallelism': 'independent DMRG runs (field scan g=1+0.02*rank), %d rank(s)' % n,
             'l2': 'working set per step (100 x (LP, RP, B) ~ 7 GB) >> 126 MB L2; no explicit flush'}
 
@@ -257,7 +273,7 @@ def run_b200(args):
     L, chi = args.L, args.chi
 
     # model: rank 0 owns the template (J, g0); NCCL broadcast, every rank patches its own field g
-    tmpl = torch.tensor([1.0, 1.0], dtype=torch.float64, device='cuda')
+    tmpl = torch.tensor([1.0, 1.0], dtype=torch.float64, device=lib.device)
     if world > 1:
         dist.broadcast(tmpl, src=0)
     J, g0 = float(tmpl[0]), float(tmpl[1])
@@ -328,9 +344,10 @@ def run_b200(args):
 
     # ---- kernel roofline probes at the centre-bond shapes (CUDA events on the launching stream)
     roof = kernel_probes(lib, chi, d, D)
+    mv_orders = matvec_order_probe(eng, psi, L, chi, d, D)
 
     # ---- gather over ranks
-    stats = torch.tensor([ms, E_final, S_mid, e2e['value'] if e2e else 0.], dtype=torch.float64, device='cuda')
+    stats = torch.tensor([ms, E_final, S_mid, e2e['value'] if e2e else 0.], dtype=torch.float64, device=lib.device)
     if world > 1:
         allst = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(allst, stats)
@@ -359,7 +376,7 @@ def run_b200(args):
             'config': workload_config(args, world), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'roofline_gemm': roof['gemm'], 'roofline_svd': roof['svd'],
             'kernel_time_shares': shares, 'kernel_family_ms_per_sweep': {k: round(v[1], 2) for k, v in prof.items()},
-            'matvec_gflops': roof['gemm']['achieved'] * 1e3, 'peaks': peaks_kind,
+            'matvec_gflops': roof['gemm']['achieved'] * 1e3, 'matvec_orders': mv_orders, 'peaks': peaks_kind,
             'result': {'E': [float(x) for x in allst[:, 1]], 'S_mid': [float(x) for x in allst[:, 2]],
                        'N_lanczos_mean': N_lan, 'svd_jacobi_sweeps_mean': float(np.mean(jsw)),
                        'svd_jacobi_sweeps_max': int(np.max(jsw)), 'svd_calls': svd_stats['calls'],
@@ -371,12 +388,48 @@ def run_b200(args):
     if not args.no_cpu:
         est = cpu_sweep_estimate(args, args.cpu_bonds)
         line['cpu_baseline'] = {'value': est['sweep_s'], 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-                                'sample': '%d centre-bond updates (oracle/dmrg_dense.py, numpy/OpenBLAS/LAPACK gesdd) '
-                                          'x %d full-chi bonds per sweep' % (args.cpu_bonds, est['full_chi_bonds']),
-                                'per_bond_s': est['per_bond_s'], 'matvec_gflops': est['matvec_gflops']}
+                                'sample': '%d centre-bond updates (oracle/dmrg_dense.py, numpy/OpenBLAS/LAPACK gesdd; '
+                                          'Lanczos matvec in the faster of the two reference contraction orders: %s) '
+                                          'x %d full-chi bonds per sweep' % (args.cpu_bonds, est['matvec_order_used'],
+                                                                             est['full_chi_bonds']),
+                                'per_bond_s': est['per_bond_s'], 'matvec_gflops': est['matvec_gflops'],
+                                'matvec_s': est['matvec_s'], 'matvec_split_s': est['matvec_split_s']}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def matvec_order_probe(eng, psi, L, chi, d, D, reps=5):
+    """TwoSiteH.matvec at the centre bond of the benchmark state in both contraction orders (the sweep uses
+    matvec_order='auto' = 'split' at this size): ms per matvec (CUDA events) and the reference-equivalent rate
+    4 D d^3 chi^3 / t.  Executed flops: combined 4 D d^3 chi^3, split 4 D d^2 chi^3 + O(chi^2)."""
+    import torch
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    out = {}
+    try:
+        i0 = L // 2 - 1
+        for order in ('combined', 'split'):
+            H = TwoSiteH(eng.env, i0, combine=True, matvec_order=order)
+            theta = H.combine_theta(psi.get_theta(i0, 2))
+            for _ in range(3):
+                H.matvec(theta)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                H.matvec(theta)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / reps
+            executed = 4. * D * d**3 * chi**3 if order == 'combined' else 4. * D * d**2 * chi**3
+            out[order] = {'ms_per_matvec': ms, 'executed_flop': executed, 'executed_tflops': executed / ms / 1e9,
+                          'reference_equivalent_tflops': 4. * D * d**3 * chi**3 / ms / 1e9}
+            del H, theta
+        out['auto_selects'] = 'split' if TwoSiteH(eng.env, i0, combine=True)._use_split(
+            TwoSiteH(eng.env, i0, combine=True).combine_theta(psi.get_theta(i0, 2))) else 'combined'
+    except Exception as e:  # a probe must never lose the bench line
+        out['error'] = repr(e)
+    return out
 
 
 def kernel_probes(lib, chi, d, D):

@@ -6,6 +6,7 @@ conservation (every Array is one dense block; BASELINE.json configs 1 and 2), wh
 with NumPy/OpenBLAS/LAPACK, function by function:
 
 * `matvec`            <- TwoSiteH.matvec, combine=True branch   (tenpy/algorithms/mps_common.py:1337-1339)
+* `matvec_split`      <- TwoSiteH.matvec, combine=False branch  (mps_common.py:1340-1350)
 * `lanczos_ground`    <- LanczosGroundState.run / _build_krylov / _converged / _calc_result_full
                          (tenpy/linalg/krylov_based.py:614, :645, :677, :160)
 * `truncate`          <- truncation.truncate                     (tenpy/linalg/truncation.py:146)
@@ -81,6 +82,18 @@ def matvec(LHeff, RHeff, theta):
     """LHeff (n, D, n) [(vR*.p0), wR, (vR.p0*)], RHeff (D, n, n) [wL, (p1*.vL), (p1.vL*)], theta (n, n)."""
     t = np.tensordot(LHeff, theta, axes=[2, 0])            # (n, D, n)
     return np.tensordot(t, RHeff, axes=[[1, 2], [0, 1]])   # (n, n)
+
+
+def matvec_split(LP, W0, W1, RP, theta4):
+    """The reference's ``combine=False`` branch of TwoSiteH.matvec (mps_common.py:1340-1350): LP, W0, W1, RP one
+    after the other.  LP (chi, D, chi) [vR*, wR, vR], W [wL, wR, p, p*], RP (chi, D, chi) [vL, wL, vL*],
+    theta4 (chi, d, d, chi) [vL, p0, p1, vR]; returns [vL, p0, p1, vR].  Same result as `matvec` on the combined
+    tensors with d times fewer flops in the chi^3 terms."""
+    t = np.tensordot(LP, theta4, axes=[2, 0])               # vR*, wR, p0, p1, vR
+    t = np.tensordot(W0, t, axes=[[0, 3], [1, 2]])          # wR, p0, vR*, p1, vR
+    t = np.tensordot(t, W1, axes=[[0, 3], [0, 3]])          # p0, vR*, vR, wR, p1
+    t = np.tensordot(t, RP, axes=[[3, 2], [1, 0]])          # p0, vR*, p1, vL*
+    return t.transpose(1, 0, 2, 3)
 
 
 def matvec_flops(n_left, D, n_right):
@@ -166,11 +179,15 @@ def update_RP(RHeff, VH):
     return np.tensordot(t, VH.conj(), axes=[2, 1])         # (chi', D, chi')
 
 
-def bond_update(LHeff, RHeff, theta, trunc_par, lanczos_par, move_right=True):
+def bond_update(LHeff, RHeff, theta, trunc_par, lanczos_par, move_right=True, matvec_fn=None):
     """One two-site update on dense tensors: Lanczos -> svd_theta -> environment update (dmrg.py:529).
 
+    `matvec_fn` (optional) replaces the combined matvec inside Lanczos (e.g. the ``combine=False`` order).
     Returns (E0, U, S, VH, new environment part, N_lanczos)."""
-    E0, th, N = lanczos_ground(lambda x: matvec(LHeff, RHeff, x), theta, **lanczos_par)
+    if matvec_fn is None:
+        def matvec_fn(x):
+            return matvec(LHeff, RHeff, x)
+    E0, th, N = lanczos_ground(matvec_fn, theta, **lanczos_par)
     U, S, VH, err, _ = svd_theta(th, trunc_par)
     env = update_LP(LHeff, U) if move_right else update_RP(RHeff, VH)
     return E0, U, S, VH, env, N

@@ -350,7 +350,8 @@ class TwoSiteDMRGEngine:
 
     def prepare_update_local(self):
         """Reference mps_common.py:498."""
-        self.eff_H = self.EffectiveH(self.env, self.i0, self.combine, self.move_right)
+        self.eff_H = self.EffectiveH(self.env, self.i0, self.combine, self.move_right,
+                                      matvec_order=self.options.get('matvec_order', 'auto'))
         theta = self.psi.get_theta(self.i0, n=2)
         return self.eff_H.combine_theta(theta)
 

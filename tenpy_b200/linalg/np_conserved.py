@@ -32,7 +32,7 @@ __all__ = ['QTYPE', 'ChargeInfo', 'LegCharge', 'LegPipe', 'Array', 'zeros', 'eye
 
 _PLAN_CACHE = {}
 svd_stats = {'calls': 0, 'jacobi_sweeps': []}   # diagnostics: Jacobi sweeps used by each npc.svd call
-_PLAN_CACHE_MAX = 4096
+_PLAN_CACHE_MAX = 16384
 
 
 def _conj_label(label):

@@ -242,3 +242,55 @@ def test_svd_extensions_host_logic(fake_device):
     assert np.max(np.abs(S - s)) < 2e-6
     assert np.max(np.abs(U.to_ndarray() @ np.diag(S) @ VH.to_ndarray() - B)) < 1e-5
     assert np.max(np.abs(VH.to_ndarray() @ VH.to_ndarray().T - np.eye(30))) < 1e-12
+
+
+def test_matvec_split_order_equals_combined(fake_device):
+    """`TwoSiteH.matvec` in the 'split' contraction order (LP, W0 W1, RP on the split theta; d times fewer flops)
+    returns the same Array as the reference's combined sequence LHeff . theta . RHeff -- dense, U(1) and U(1)xU(1)"""
+    from tenpy_b200.models import TFIChain, SpinChain, FermiHubbardChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg import np_conserved as npc
+    cases = [(TFIChain({'L': 8, 'J': 1., 'g': 1.1, 'conserve': None}), ['up'] * 8, None),
+             (SpinChain({'L': 8, 'Jx': 1., 'Jy': 1., 'Jz': 0.7, 'conserve': 'Sz'}), ['up', 'down'] * 4, True),
+             (FermiHubbardChain({'L': 6, 't': 1., 'U': 4., 'mu': 0.}), ['up', 'down'] * 3, True)]
+    for M, state, mixer in cases:
+        psi = MPS.from_product_state(M.lat_sites, state)
+        eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': mixer, 'combine': True, 'matvec_order': 'combined',
+                                              'trunc_params': {'chi_max': 24, 'svd_min': 1e-12}})
+        eng.sweep()
+        eng.sweep()
+        L = psi.L
+        for i0 in range(L - 1):
+            Hc = TwoSiteH(eng.env, i0, combine=True, matvec_order='combined')
+            Hs = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+            theta = Hc.combine_theta(psi.get_theta(i0, 2))
+            a, b = Hc.matvec(theta), Hs.matvec(theta)
+            assert a.get_leg_labels() == b.get_leg_labels()
+            assert npc.norm(a - b) <= 1e-13 * max(npc.norm(a), 1e-300)
+        # 'auto' picks the combined order for these small blocks, and 'split' once the threshold is lowered
+        Ha = TwoSiteH(eng.env, L // 2 - 1, combine=True)
+        th = Ha.combine_theta(psi.get_theta(L // 2 - 1, 2))
+        assert not Ha._use_split(th)
+        Ha.SPLIT_MIN_BLOCK = 1
+        assert Ha._use_split(th)
+
+
+def test_dmrg_driver_split_matvec(fake_device):
+    """the whole DMRG run with matvec_order='split' reproduces the reference goldens (TFI config 1 and XXZ-Sz)"""
+    from tenpy_b200.models import TFIChain, SpinChain
+    g = h.load('dmrg.npz')
+    M = TFIChain({'L': 20, 'J': 1., 'g': 1., 'conserve': None})
+    res, psi = _run_dmrg(M, ['up'] * 20, {'mixer': None, 'max_E_err': 1e-10, 'combine': True, 'matvec_order': 'split',
+                                         'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
+    assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
+    assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
+    L = 16
+    M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 1., 'conserve': 'Sz'})
+    opts = {'mixer': True, 'mixer_params': {'amplitude': 1e-5, 'decay': 2., 'disable_after': 6}, 'max_E_err': 1e-11,
+            'max_S_err': 1e-8, 'trunc_params': {'chi_max': 60, 'svd_min': 1e-10}, 'combine': True, 'max_sweeps': 20,
+            'matvec_order': 'split'}
+    res, psi = _run_dmrg(M, ['up', 'down'] * (L // 2), opts)
+    assert abs(res['E'] - g['xxz_E']) < 1e-10 * abs(g['xxz_E'])
+    assert np.max(np.abs(psi.entanglement_entropy() - g['xxz_S'])) < 1e-7

@@ -133,3 +133,18 @@ def test_lanczos_dense():
         w, v = np.linalg.eigh(Hm)
         assert abs(E0 - w[0]) < 1e-10
         assert abs(abs(np.dot(psi, v[:, 0])) - 1.) < 1e-8
+
+
+def test_dense_matvec_orders_agree():
+    """the two contraction orders of TwoSiteH.matvec in the reference (combine=True :1337, combine=False :1340)
+    are the same linear map; pins `od.matvec_split` on `od.matvec` (itself pinned on the golden vectors above)"""
+    rng = np.random.default_rng(5)
+    chi_l, chi_r, d, D = 7, 5, 2, 3
+    LP = rng.standard_normal((chi_l, D, chi_l))
+    RP = rng.standard_normal((chi_r, D, chi_r))
+    W0 = od.tfi_mpo(1.3, 0.7)
+    W1 = rng.standard_normal((D, D, d, d))
+    theta = rng.standard_normal((chi_l, d, d, chi_r))
+    a = od.matvec(od.contract_LHeff(LP, W0), od.contract_RHeff(RP, W1), theta.reshape(chi_l * d, d * chi_r))
+    b = od.matvec_split(LP, W0, W1, RP, theta).reshape(chi_l * d, d * chi_r)
+    assert np.max(np.abs(a - b)) < 1e-13 * np.max(np.abs(a))
