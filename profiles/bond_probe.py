@@ -24,6 +24,7 @@ ap.add_argument('--L', type=int, default=22)
 ap.add_argument('--chi', type=int, default=1024)
 ap.add_argument('--bonds', type=int, default=1)
 ap.add_argument('--lanczos-N', type=int, default=10)
+ap.add_argument('--warm-sweeps', type=int, default=3, help='as bench.py: 3 untimed warm-up sweeps')
 args = ap.parse_args()
 torch.cuda.set_device(0)
 lib = backend.get_lib()
@@ -34,7 +35,8 @@ eng = dmrg.TwoSiteDMRGEngine(psi, model, {
     'mixer': None, 'combine': True, 'diag_method': 'lanczos', 'svd_warm_start': False,
     'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None},
     'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N}})
-eng.sweep()
+for _ in range(args.warm_sweeps):
+    eng.sweep()
 torch.cuda.synchronize()
 first = L // 2 - 1 - (args.bonds - 1) // 2
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

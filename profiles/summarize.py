@@ -10,7 +10,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 GO = os.path.join(os.path.dirname(OUT), 'gpurun_out')
 
 
-def launches(tag='r01'):
+def launches(tag='r01', what=None, command=None):
     path = os.path.join(GO, tag + '_launches.csv')
     rows = []
     with open(path) as f:
@@ -31,10 +31,10 @@ def launches(tag='r01'):
         tot[key][1] += ns
     total = sum(v[1] for v in tot.values())
     with open(os.path.join(OUT, tag + '_launch_shares.md'), 'w') as f:
-        f.write('# %s: per-kernel device time of the timed bench step (ncu gpu__time_duration.sum, serialised, '
-                'cold cache: compare SHARES)\n\n' % tag)
-        f.write('command: `ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off '
-                'python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu`\n\n')
+        f.write('# %s: per-kernel device time of %s (ncu gpu__time_duration.sum, serialised, '
+                'cold cache: compare SHARES)\n\n' % (tag, what or 'the timed bench step'))
+        f.write('command: `%s`\n\n' % (command or 'ncu --metrics gpu__time_duration.sum --clock-control none '
+                                        '--profile-from-start off python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu'))
         f.write('| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|\n')
         for k, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             f.write('| `%s` | %d | %.1f | %.3f | %.1f |\n' % (k, n, ns / 1e6, ns / total, ns / n / 1e3))
@@ -74,6 +74,13 @@ def full(tag, name):
 
 if __name__ == '__main__':
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
-    launches(tag)
-    full(tag, 'gemm')
-    full(tag, 'jacobi')
+    if tag == 'r01d':
+        launches(tag, 'ONE centre-bond update at chi=1024 (10 Lanczos matvecs in the split order, block SVD, '
+                      'environment update) after 3 warm-up sweeps',
+                 'ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off '
+                 'python profiles/bond_probe.py --bonds 1  (profiles/capture_r01d.sh)')
+        full(tag, 'bond')
+    else:
+        launches(tag)
+        full(tag, 'gemm')
+        full(tag, 'jacobi')

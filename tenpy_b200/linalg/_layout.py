@@ -64,7 +64,7 @@ class BlockLayout:
     A cache entry that also depends on leg data not visible in the block table (pipes) has to carry
     ``LegCharge.content_key()`` of those legs in its key.
     """
-    __slots__ = ('qdata', 'shapes', 'sizes', 'offsets', 'size', 'uid', 'rank', 'nblocks', 'cache')
+    __slots__ = ('qdata', 'shapes', 'sizes', 'offsets', 'size', 'uid', 'rank', 'nblocks', 'cache', 'has_padding')
 
     def __new__(cls, qdata, shapes):
         qdata = np.ascontiguousarray(qdata, dtype=np.int64)
@@ -83,6 +83,7 @@ class BlockLayout:
         self.nblocks, self.rank = qdata.shape
         self.sizes = np.prod(shapes, axis=1, dtype=np.int64) if self.rank else np.ones(self.nblocks, np.int64)
         self.offsets, self.size = _aligned_offsets(self.sizes)
+        self.has_padding = bool(np.any(self.sizes % ALIGN))
         self.uid = next(_uid)
         self.cache = {}
         if len(_INTERN) >= _INTERN_MAX:

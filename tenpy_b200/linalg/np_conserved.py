@@ -440,7 +440,7 @@ class Array:
             old_layout.cache[key] = cached
         new_layout, rec, rec_dev = cached
         if old_layout.nblocks:
-            buf = backend.zeros(new_layout.size)
+            buf = _dest_buffer(new_layout, rec)
             backend.get_lib().copy_blocks(rec, rec_dev, self._buf, buf)
             self._buf = buf
         self._layout = new_layout
@@ -702,7 +702,7 @@ class Array:
             cached = (new_layout, rec, backend.to_device(rec), pipes)
             lay.cache[key] = cached
         new_layout, rec, rec_dev = cached[:3]
-        buf = backend.zeros(new_layout.size)
+        buf = _dest_buffer(new_layout, rec)
         backend.get_lib().copy_blocks(rec, rec_dev, self._buf, buf)
         res._set_blocks(new_layout, buf)
         return res
@@ -746,7 +746,7 @@ class Array:
             cached = (new_layout, rec, backend.to_device(rec))
             lay.cache[key] = cached
         new_layout, rec, rec_dev = cached
-        buf = backend.zeros(new_layout.size)
+        buf = _dest_buffer(new_layout, rec)
         backend.get_lib().copy_blocks(rec, rec_dev, self._buf, buf)
         res._set_blocks(new_layout, buf)
         return res
@@ -943,10 +943,18 @@ def tensordot(a, b, axes=2):
     plan, lay_c = cached[2], cached[3]
     if lay_c is None:
         return res
-    buf = backend.zeros(lay_c.size) if np.any(lay_c.sizes % 16) else backend.empty(lay_c.size)
+    buf = backend.zeros(lay_c.size) if lay_c.has_padding else backend.empty(lay_c.size)
     plan.run(a._buf, b._buf, buf)
     res._set_blocks(lay_c, buf)
     return res
+
+
+def _dest_buffer(layout, rec):
+    """destination buffer of a block move: zero-filled unless the copy records `rec` cover every element of every
+    block and the layout has no alignment padding (then the fill launch is skipped)"""
+    if not layout.has_padding and len(rec) and int(rec[:, 2].sum()) == int(layout.sizes.sum()):
+        return backend.empty(layout.size)
+    return backend.zeros(layout.size)
 
 
 def _labels_unique(labels):

@@ -38,7 +38,12 @@ def gpu_lib():
 def fake_device():
     from tenpy_b200 import backend
     from fake_device import FakeDeviceLib
+    import torch
     old = backend._state['lib']
     lib = backend.use_library(FakeDeviceLib())
+    # poison uninitialised buffers: any element the host logic forgets to write shows up as NaN in the results
+    old_empty = backend.empty
+    backend.empty = lambda n: torch.full((int(n),), float('nan'), dtype=torch.float64)
     yield lib
+    backend.empty = old_empty
     backend.use_library(old)
