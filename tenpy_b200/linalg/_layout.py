@@ -24,7 +24,7 @@ import numpy as np
 from .charges import _lexsort_rows, _row_change_points
 
 __all__ = ['BlockLayout', 'ALIGN', 'COPY_REC', 'COPY_MAXRANK', 'plan_transpose', 'plan_combine', 'plan_split',
-           'plan_project', 'plan_scale_axis']
+           'plan_project', 'plan_scale_axis', 'plan_take_slice', 'plan_add_leg', 'plan_concatenate']
 
 ALIGN = 16
 COPY_REC = 22
@@ -357,3 +357,56 @@ def plan_scale_axis(layout, leg, axis):
     rec[:, 3] = np.prod(layout.shapes[:, axis + 1:], axis=1)
     rec[:, 4] = leg.slices[layout.qdata[:, axis]]
     return rec
+
+
+def plan_take_slice(layout, axes, qidx, ridx):
+    """``A[..., i, ...]`` on the block level (reference `Array.take_slice`, np_conserved.py:1037): keep the blocks
+    whose qindex on `axes` equals `qidx`, take index `ridx` (inside the block) there and drop these legs.
+
+    Returns ``(new_layout, records)``."""
+    axes = [int(a) for a in axes]
+    keep_axes = [a for a in range(layout.rank) if a not in axes]
+    keep = np.all(layout.qdata[:, axes] == np.asarray(qidx, dtype=np.int64)[None, :], axis=1)
+    idx = np.nonzero(keep)[0]
+    # dropping columns that are constant over the kept rows preserves the lex order
+    new = BlockLayout(layout.qdata[np.ix_(idx, keep_axes)], layout.shapes[np.ix_(idx, keep_axes)])
+    st = layout.strides()[idx]
+    soff = layout.offsets[idx] + (st[:, axes] * np.asarray(ridx, dtype=np.int64)[None, :]).sum(axis=1)
+    rec = _copy_records(soff, new.offsets, new.shapes, st[:, keep_axes], new.strides())
+    return new, rec
+
+
+def plan_add_leg(layout, axis, qi, ri, block_size):
+    """Insert a leg before `axis` and put the data at index (`qi`, `ri`) of it (reference `Array.add_leg`,
+    np_conserved.py:1130).  Returns ``(new_layout, records)``; the destination has to be zero-filled."""
+    qd = np.insert(layout.qdata, axis, int(qi), axis=1)
+    sh = np.insert(layout.shapes, axis, int(block_size), axis=1)
+    new = BlockLayout(qd, sh)            # a constant column keeps the lex order
+    nst = new.strides()
+    old_axes = [a for a in range(new.rank) if a != axis]
+    doff = new.offsets + int(ri) * nst[:, axis]
+    rec = _copy_records(layout.offsets, doff, layout.shapes, layout.strides(), nst[:, old_axes])
+    return new, rec
+
+
+def plan_concatenate(layouts, legs, axis, shifts):
+    """Stack block tables along `axis` (reference `concatenate`, np_conserved.py:3027): the blocks are unchanged, the
+    qindex on `axis` of array j is shifted by ``shifts[j]``; the result table is lex-sorted.
+
+    Returns ``(new_layout, [records of array 0, records of array 1, ...])`` (flat 1-D copies)."""
+    qd = []
+    for lay, sh in zip(layouts, shifts):
+        q = lay.qdata.copy()
+        q[:, axis] += int(sh)
+        qd.append(q)
+    qd = np.concatenate(qd, axis=0)
+    new, perm = BlockLayout.from_legs(legs, qd)
+    inv = np.empty(len(perm), dtype=np.int64)
+    inv[perm] = np.arange(len(perm))
+    recs, at = [], 0
+    for lay in layouts:
+        tgt = inv[at:at + lay.nblocks]
+        at += lay.nblocks
+        recs.append(_copy_records(lay.offsets, new.offsets[tgt], lay.sizes[:, None], np.ones((lay.nblocks, 1), np.int64),
+                                  np.ones((lay.nblocks, 1), np.int64)))
+    return new, recs

@@ -374,6 +374,20 @@ class LegCharge:
         map_qind[keep] = np.arange(len(keep), dtype=np.intp)
         return map_qind, block_masks, res
 
+    def extend(self, extra):
+        """New LegCharge with the blocks of `extra` (a LegCharge, or an int = one block of zero charge) appended
+        (reference charges.py:1336)."""
+        if not isinstance(extra, LegCharge):
+            extra = LegCharge.from_trivial(extra, self.chinfo, self.qconj)
+        bn = self.block_number
+        new_slices = np.zeros(bn + extra.block_number + 1, np.intp)
+        new_slices[:bn + 1] = self.slices
+        new_slices[bn:] = extra.slices + self.ind_len
+        new_charges = np.zeros((bn + extra.block_number, self.chinfo.qnumber), dtype=QTYPE)
+        new_charges[:bn] = self.charges
+        new_charges[bn:] = extra.charges if self.qconj == extra.qconj else self.chinfo.make_valid(-extra.charges)
+        return LegCharge(self.chinfo, new_slices, new_charges, qconj=self.qconj)
+
     def charge_sectors(self):
         """Unique charge rows."""
         return np.unique(self.charges, axis=0)

@@ -24,11 +24,13 @@ import numpy as np
 
 from . import charges
 from .charges import ChargeInfo, LegCharge, LegPipe, QTYPE, _lexsort_rows
-from ._layout import (BlockLayout, plan_transpose, plan_combine, plan_split, plan_project, plan_scale_axis)
+from ._layout import (BlockLayout, plan_transpose, plan_combine, plan_split, plan_project, plan_scale_axis,
+                      plan_take_slice, plan_add_leg, plan_concatenate)
 from .. import backend
 
 __all__ = ['QTYPE', 'ChargeInfo', 'LegCharge', 'LegPipe', 'Array', 'zeros', 'eye_like', 'diag', 'tensordot',
-           'inner', 'norm', 'svd', 'eigh', 'outer', 'trace', 'to_iterable_arrays', 'pinv', 'concatenate_qdata']
+           'inner', 'norm', 'svd', 'eigh', 'eigvalsh', 'outer', 'trace', 'to_iterable_arrays', 'pinv', 'concatenate_qdata',
+           'concatenate', 'ones', 'detect_qtotal']
 
 _PLAN_CACHE = {}
 svd_stats = {'calls': 0, 'jacobi_sweeps': []}   # diagnostics: Jacobi sweeps used by each npc.svd call
@@ -824,6 +826,88 @@ class Array:
         res._layout = BlockLayout(np.ascontiguousarray(lay.qdata[:, keep]), np.ascontiguousarray(lay.shapes[:, keep]))
         return res
 
+    def take_slice(self, indices, axes):
+        """``A.take_slice([i, j], [1, 2])`` = ``A[:, i, j, :]`` (reference npc:1037): the legs `axes` are removed,
+        their charges at the given indices are subtracted from `qtotal`.  One strided block-copy launch."""
+        axes = self.get_leg_indices(list(axes) if isinstance(axes, (list, tuple, np.ndarray)) else [axes])
+        indices = np.atleast_1d(np.asarray(indices, dtype=np.intp))
+        if len(axes) != len(indices):
+            raise ValueError('len(axes) != len(indices)')
+        if indices.ndim != 1:
+            raise ValueError('indices may only contain ints')
+        if len(axes) == 0:
+            return self.copy(deep=True)
+        pos = np.array([self.legs[a].get_qindex(int(i)) for a, i in zip(axes, indices)], dtype=np.int64)
+        keep_axes = [a for a in range(self.rank) if a not in axes]
+        qtotal = self.qtotal.copy()
+        for a, (qi, _) in zip(axes, pos):
+            qtotal = qtotal - self.legs[a].get_charge(int(qi))
+        res = Array([self.legs[a] for a in keep_axes], self.dtype, self.chinfo.make_valid(qtotal),
+                    [self._labels[a] for a in keep_axes])
+        lay = self._layout
+        if lay.nblocks == 0:
+            return res
+        new_layout, rec = plan_take_slice(lay, axes, pos[:, 0], pos[:, 1])
+        if new_layout.nblocks:
+            buf = _dest_buffer(new_layout, rec)
+            backend.get_lib().copy_blocks(rec, backend.to_device(rec), self._buf, buf)
+            res._set_blocks(new_layout, buf)
+        return res
+
+    def add_leg(self, leg, i, axis=0, label=None):
+        """Copy with the new `leg` inserted before `axis`; ``result.take_slice(i, axis)`` is `self`, all other
+        entries are zero, `qtotal` grows by the charge of index `i` (reference npc:1130)."""
+        if axis < 0:
+            axis += self.rank
+        legs = list(self.legs)
+        legs.insert(axis, leg)
+        qi, ri = leg.get_qindex(int(i))
+        labels = list(self._labels)
+        if label is not None and label in labels:
+            raise ValueError('label already exists')
+        labels.insert(axis, label)
+        res = Array(legs, self.dtype, self.chinfo.make_valid(self.qtotal + leg.get_charge(qi)))
+        res._labels = labels
+        lay = self._layout
+        if lay.nblocks == 0:
+            return res
+        new_layout, rec = plan_add_leg(lay, axis, qi, ri, leg.get_block_sizes()[qi])
+        buf = backend.zeros(new_layout.size)
+        backend.get_lib().copy_blocks(rec, backend.to_device(rec), self._buf, buf)
+        return res._set_blocks(new_layout, buf)
+
+    def extend(self, axis, extra):
+        """Increase the dimension of `axis` by the blocks of `extra` (LegCharge or int), filled with zeros
+        (reference npc:1172).  The stored blocks do not change."""
+        res = self.copy(deep=True)
+        ax = self.get_leg_index(axis)
+        res.legs[ax] = res.legs[ax].extend(extra)
+        res._set_shape()
+        return res
+
+    def iswapaxes(self, axis1, axis2):
+        """Swap two legs in place (reference npc:2090)."""
+        a1, a2 = self.get_leg_indices([axis1, axis2])
+        perm = list(range(self.rank))
+        perm[a1], perm[a2] = a2, a1
+        return self.itranspose(perm)
+
+    def is_completely_blocked(self):
+        """Reference npc:1368."""
+        return all(l.is_blocked() for l in self.legs)
+
+    def isort_qdata(self):
+        """The block table of a packed Array is always lex-sorted (reference npc:1431): nothing to do."""
+        return self
+
+    def complex_conj(self):
+        """Complex conjugate without touching the charges (reference npc:2237); real data: a copy."""
+        return self.copy(deep=True)
+
+    def matvec(self, other):
+        """``tensordot(self, other, axes=1)`` (reference npc:2364); lets a 2D Array act as a linear operator."""
+        return tensordot(self, other, axes=1)
+
     def __repr__(self):
         return '<npc.Array shape={0!s} labels={1!s} blocks={2:d}>'.format(self.shape, self._labels,
                                                                          self.stored_blocks)
@@ -855,6 +939,56 @@ def _union_layout(legs, a, b):
 def zeros(legcharges, dtype=np.float64, qtotal=None, labels=None):
     """Array without stored blocks (reference npc:3108)."""
     return Array(legcharges, dtype, qtotal, labels)
+
+
+def ones(legcharges, dtype=np.float64, qtotal=None, labels=None):
+    """All charge-allowed blocks filled with ones (reference npc:2969)."""
+    return Array.from_func(np.ones, legcharges, dtype, qtotal, labels=labels)
+
+
+def detect_qtotal(flat_array, legcharges, cutoff=None):
+    """Total charge of the sector of the largest entry of a dense array (reference npc:3346)."""
+    return Array.detect_qtotal(flat_array, legcharges, cutoff)
+
+
+def concatenate(arrays, axis=0, copy=True):
+    """Stack Arrays along `axis` like ``np.concatenate`` (reference npc:3027): the leg is the concatenation of the
+    legs (neither sorted nor bunched), every stored block stays a block; labels from the first array."""
+    arrays = list(arrays)
+    first = arrays[0]
+    axis = first.get_leg_index(axis)
+    not_axis = [a for a in range(first.rank) if a != axis]
+    for a in arrays:
+        if a.shape[:axis] != first.shape[:axis] or a.shape[axis + 1:] != first.shape[axis + 1:]:
+            raise ValueError('wrong shape to fit ' + repr(a.shape) + ' into ' + repr(first.shape))
+        if a.chinfo != first.chinfo:
+            raise ValueError('wrong ChargeInfo')
+        if np.any(a.qtotal != first.qtotal):
+            raise ValueError('wrong qtotal')
+        for l in not_axis:
+            a.legs[l].test_equal(first.legs[l])
+    axis_qconj = first.legs[axis].qconj
+    sizes, chs, shifts, shift = [], [], [], 0
+    for a in arrays:
+        leg = a.legs[axis]
+        sizes.extend(leg.get_block_sizes())
+        chs.append(leg.charges if leg.qconj == axis_qconj else first.chinfo.make_valid(-leg.charges))
+        shifts.append(shift)
+        shift += leg.block_number
+    new_leg = LegCharge.from_qind(first.chinfo, np.append([0], np.cumsum(sizes)), np.concatenate(chs, axis=0), axis_qconj)
+    legs = list(first.legs)
+    legs[axis] = new_leg
+    res = Array(legs, np.float64, first.qtotal)
+    res._labels = list(first._labels)
+    new_layout, recs = plan_concatenate([a._layout for a in arrays], legs, axis, shifts)
+    if new_layout.nblocks == 0:
+        return res
+    buf = backend.zeros(new_layout.size) if new_layout.has_padding else backend.empty(new_layout.size)
+    lib = backend.get_lib()
+    for a, rec in zip(arrays, recs):
+        if len(rec):
+            lib.copy_blocks(rec, backend.to_device(rec), a._buf, buf)
+    return res._set_blocks(new_layout, buf)
 
 
 def diag(s, leg, dtype=None, labels=None):
@@ -1326,6 +1460,11 @@ def pinv(a, cutoff=1.e-15):
     VH.iscale_axis(1. / S, 0)
     res = tensordot(VH.conj().itranspose(), U.conj().itranspose(), axes=1)
     return res.iset_leg_labels([labels[1], labels[0]]) if _labels_unique([labels[1], labels[0]]) else res
+
+
+def eigvalsh(a, UPLO='L', sort=None):
+    """Eigenvalues of a hermitian 2D Array (reference npc:3972)."""
+    return eigh(a, UPLO, sort)[0]
 
 
 def eigh(a, UPLO='L', sort=None):
