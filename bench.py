@@ -111,11 +111,29 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ CPU (oracle) arm
+def _use_all_host_threads():
+    """BLAS/LAPACK on every host core, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get('num_threads', 1)) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count()
+
+
 def cpu_bond_sample(chi, d, D, lanczos_N, n_bonds, seed=0):
     """time `n_bonds` two-site updates at the chain centre (full chi) with the dense CPU oracle, once with the
     reference's default matvec (combine=True: LHeff.theta.RHeff) and once with its combine=False contraction order
     inside Lanczos (d times fewer flops); the faster one is the CPU baseline."""
     from oracle import dmrg_dense as od
+    _use_all_host_threads()
     rng = np.random.default_rng(seed)
     n = chi * d
     LP = rng.standard_normal((chi, D, chi))
@@ -169,7 +187,6 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count()
     vals = []
     for it in range(args.warmup + args.steps):
         est = cpu_sweep_estimate(args, 1)
@@ -183,7 +200,7 @@ def run_reference(args):
             'warmup': args.warmup, 'ms_per_step': v * 1e3, 'higher_is_better': False, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
             'config': workload_config(args, 1),
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port', 'sample': sample,
                              'matvec_gflops': float(np.mean([e['matvec_gflops'] for e in vals])),
                              'matvec_s': vals[0]['matvec_s'], 'matvec_split_s': vals[0]['matvec_split_s']},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -349,6 +366,7 @@ def run_b200(args):
     # ---- kernel roofline probes at the centre-bond shapes (CUDA events on the launching stream)
     roof = kernel_probes(lib, chi, d, D)
     mv_orders = matvec_order_probe(eng, psi, L, chi, d, D)
+    roof['svd']['workload_theta'] = svd_theta_probe(eng, psi, L)
 
     # ---- gather over ranks
     stats = torch.tensor([ms, E_final, S_mid, e2e['value'] if e2e else 0.], dtype=torch.float64, device=lib.device)
@@ -391,7 +409,7 @@ def run_b200(args):
                        if sub_stats['residuals'] else None}}
     if not args.no_cpu:
         est = cpu_sweep_estimate(args, args.cpu_bonds)
-        line['cpu_baseline'] = {'value': est['sweep_s'], 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+        line['cpu_baseline'] = {'value': est['sweep_s'], 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
                                 'sample': '%d centre-bond updates (oracle/dmrg_dense.py, numpy/OpenBLAS/LAPACK gesdd; '
                                           'Lanczos matvec in the faster of the two reference contraction orders: %s) '
                                           'x %d full-chi bonds per sweep' % (args.cpu_bonds, est['matvec_order_used'],
@@ -441,6 +459,38 @@ def matvec_order_probe(eng, psi, L, chi, d, D, reps=5):
     except Exception as e:  # a probe must never lose the bench line
         out['error'] = repr(e)
     return out
+
+
+def svd_theta_probe(eng, psi, L, reps=3):
+    """block SVD (npc.svd with the sweep's deflation tolerance) of the two-site wave function at the centre bond of the
+    benchmark state -- the matrix the sweep actually decomposes (numerically low rank once DMRG has converged), next
+    to the generic full-rank block of `roofline_svd`."""
+    import torch
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg import np_conserved as npc
+    try:
+        i0 = L // 2 - 1
+        H = TwoSiteH(eng.env, i0, combine=True)
+        theta = H.combine_theta(psi.get_theta(i0, 2))
+        tol = eng.trunc_params.get('svd_deflation_tol', 1.e-10)
+        chi_max = eng.trunc_params.get('chi_max', None)
+        U, S, VH = npc.svd(theta, inner_labels=['vR', 'vL'], deflation_tol=tol, n_keep=chi_max)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        n0 = len(npc.svd_stats['jacobi_sweeps'])
+        ev0.record()
+        for _ in range(reps):
+            npc.svd(theta, inner_labels=['vR', 'vL'], deflation_tol=tol, n_keep=chi_max)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / reps
+        m, n = theta.shape
+        by = 8. * (m * n + m * min(m, n) + min(m, n) + min(m, n) * n)
+        return {'shape': [int(m), int(n)], 'ms_per_svd': ms, 'GB/s_algorithmic': by / ms / 1e6,
+                'jacobi_sweeps': npc.svd_stats['jacobi_sweeps'][n0:],
+                'rank_above_1e-10': int(np.sum(S > 1e-10 * S.max())), 'rank_above_1e-8': int(np.sum(S > 1e-8 * S.max()))}
+    except Exception as e:  # a probe must never lose the bench line
+        return {'error': repr(e)}
 
 
 def kernel_probes(lib, chi, d, D):
