@@ -19,11 +19,11 @@ from ..linalg import np_conserved as npc
 from ..linalg.krylov_based import LanczosGroundState
 from ..linalg.truncation import svd_theta, TruncationError
 from ..networks.mpo import MPOEnvironment
-from .mps_common import TwoSiteH, DensityMatrixMixer
+from .mps_common import OneSiteH, TwoSiteH, DensityMatrixMixer
 
 logger = logging.getLogger(__name__)
 
-__all__ = ['run', 'TwoSiteDMRGEngine', 'chi_list', 'entropy', 'full_diag_effH']
+__all__ = ['run', 'TwoSiteDMRGEngine', 'SingleSiteDMRGEngine', 'chi_list', 'entropy', 'full_diag_effH']
 
 
 def entropy(p, n=1):
@@ -51,10 +51,17 @@ def chi_list(chi_max, dchi=20, nsweeps=20):
 
 
 def run(psi, model, options):
-    """Run two-site DMRG; `psi` is optimised in place (reference dmrg.py:63).
+    """Run DMRG; `psi` is optimised in place (reference dmrg.py:63).  ``options['active_sites']`` (default 2) selects
+    :class:`TwoSiteDMRGEngine` or :class:`SingleSiteDMRGEngine`.
 
     Returns a dict with ``E``, ``shelve``, ``bond_statistics``, ``sweep_statistics``."""
-    engine = TwoSiteDMRGEngine(psi, model, options)
+    active_sites = dict(options or {}).get('active_sites', 2)
+    if active_sites == 1:
+        engine = SingleSiteDMRGEngine(psi, model, options)
+    elif active_sites == 2:
+        engine = TwoSiteDMRGEngine(psi, model, options)
+    else:
+        raise ValueError('For DMRG, can only use 1 or 2 active sites, not {0!r}'.format(active_sites))
     E, _ = engine.run()
     return {'E': E, 'shelve': False, 'bond_statistics': engine.update_stats,
             'sweep_statistics': engine.sweep_stats}
@@ -313,7 +320,7 @@ class TwoSiteDMRGEngine:
 
     # ------------------------------------------------------------------ one sweep (mps_common.py:345)
     def get_sweep_schedule(self):
-        L, n = self.psi.L, 2
+        L, n = self.psi.L, self.n_optimize
         assert L > n
         i0s = list(range(0, L - n)) + list(range(L - n, 0, -1))
         move_right = [True] * (L - n) + [False] * (L - n)
@@ -352,20 +359,21 @@ class TwoSiteDMRGEngine:
         """Reference mps_common.py:498."""
         self.eff_H = self.EffectiveH(self.env, self.i0, self.combine, self.move_right,
                                       matvec_order=self.options.get('matvec_order', 'auto'))
-        theta = self.psi.get_theta(self.i0, n=2)
+        theta = self.psi.get_theta(self.i0, n=self.n_optimize)
         return self.eff_H.combine_theta(theta)
 
     def update_local(self, theta, optimize=True):
         """Reference dmrg.py:529."""
         i0 = self.i0
-        age = self.env.get_LP_age(i0) + 2 + self.env.get_RP_age(i0 + 1)
+        n_opt = self.n_optimize
+        age = self.env.get_LP_age(i0) + n_opt + self.env.get_RP_age(i0 + n_opt - 1)
         if optimize:
             E0, theta, N, ov_change = self.diag(theta)
         else:
             E0, N, ov_change = None, 0, 0.
         theta = self.prepare_svd(theta)
         U, S, VH, err, S_approx = self.mixed_svd(theta)
-        self._entropy_approx[i0 + 1] = entropy(np.asarray(S_approx)**2)
+        self._entropy_approx[(i0 + n_opt - 1) % self.psi.L] = entropy(np.asarray(S_approx)**2)
         self.set_B(U, S, VH)
         return {'E0': E0, 'err': err, 'N': N, 'age': age, 'U': U, 'VH': VH, 'ov_change': ov_change}
 
@@ -413,33 +421,39 @@ class TwoSiteDMRGEngine:
         VH.ireplace_label('(p1.vR)', '(p.vR)')
         return U, S, VH, err, S_a
 
+    def _update_env_inds(self):
+        """left and right updated site (reference mps_common.py:591)"""
+        if self.n_optimize == 2 or self.move_right:
+            return self.i0, self.i0 + 1
+        return self.i0 - 1, self.i0
+
     def set_B(self, U, S, VH):
-        """Reference dmrg.py:934."""
+        """Reference dmrg.py:934 / :1112."""
+        i_L, i_R = self._update_env_inds()
         B0 = U.split_legs(['(vL.p)'])
         B1 = VH.split_legs(['(p.vR)'])
-        i0 = self.i0
-        self.psi.set_B(i0, B0, form='A')
-        self.psi.set_B(i0 + 1, B1, form='B')
-        self.psi.set_SR(i0, S)
+        self.psi.set_B(i_L, B0, form='A')
+        self.psi.set_B(i_R, B1, form='B')
+        self.psi.set_SR(i_L, S)
 
     def update_env(self, **update_data):
         """Reference mps_common.py:569: the parts across the updated bond are dropped, the one needed next is
         recomputed from `LHeff` / `RHeff` (TwoSiteH.update_LP / update_RP)."""
-        i0 = self.i0
-        self.env.del_LP(i0 + 1)
-        self.env.del_RP(i0)
+        i_L, i_R = self._update_env_inds()
+        self.env.del_LP(i_R)
+        self.env.del_RP(i_L)
         update_LP, update_RP = self.update_LP_RP
         if update_LP:
-            self.eff_H.update_LP(self.env, i0 + 1, update_data['U'])
+            self.eff_H.update_LP(self.env, i_R, update_data['U'])
         if update_RP:
-            self.eff_H.update_RP(self.env, i0, update_data['VH'])
+            self.eff_H.update_RP(self.env, i_L, update_data['VH'])
 
     def post_update_local(self, E0, age, N, ov_change, err, **update_data):
         """Reference dmrg.py:575."""
         i0 = self.i0
         E_trunc = None
         if self._meas_E_trunc or E0 is None:
-            E_trunc = float(self.env.full_contraction(i0))    # uses the updated LP / RP
+            E_trunc = float(self.env.full_contraction(self._update_env_inds()[0]))    # uses the updated LP / RP
             if E0 is None:
                 E0 = E_trunc
             E_trunc = E_trunc - E0
@@ -456,10 +470,88 @@ class TwoSiteDMRGEngine:
 
     def free_no_longer_needed_envs(self):
         """Reference mps_common.py:614: parts that will be recomputed before their next use are dropped."""
-        i0 = self.i0
+        i_L, i_R = self._update_env_inds()
         update_LP, update_RP = self.update_LP_RP
-        if update_RP:
-            self.env.del_LP(i0)                               # will update (i0-1, i0) next: LP[i0] is useless
-        if update_LP:
-            self.env.del_RP(i0 + 1)                           # will update (i0+1, i0+2) next: RP[i0+1] is useless
+        if self.n_optimize == 2:
+            if update_RP:
+                self.env.del_LP(i_L)                          # will update (i0-1, i0) next: LP[i0] is useless
+            if update_LP:
+                self.env.del_RP(i_R)                          # will update (i0+1, i0+2) next: RP[i0+1] is useless
+        else:
+            if self.move_right and update_RP:
+                self.env.del_LP(i_L)
+            elif (self.move_right is False) and update_LP:
+                self.env.del_RP(i_R)
         self.eff_H = None
+
+
+class SingleSiteDMRGEngine(TwoSiteDMRGEngine):
+    """Engine of the single-site DMRG (reference dmrg.py:955): one site is optimised at a time, the effective
+    Hamiltonian is :class:`~tenpy_b200.algorithms.mps_common.OneSiteH` (``LP--W0--RP``, dense matvec cost
+    ``O(D d chi^3)``), `theta` is split by an SVD whose non-isometric factor is absorbed into the next site.
+
+    Mixers: ``None``, or :class:`DensityMatrixMixer`, which cannot decompose a one-site wave function and therefore
+    works on the two-site `theta` (two-site cost for the mixing step, as the reference warns, dmrg.py:1128).  The
+    reference's default one-site mixer (`SubspaceExpansion`, mps_common.py:2082) is not part of this build; without
+    a mixer the bond dimensions (and charge sectors) of the initial state cannot grow."""
+    EffectiveH = OneSiteH
+    DefaultMixer = DensityMatrixMixer
+    n_optimize = 1
+
+    def prepare_svd(self, theta):
+        """`'p'` has to point away from the direction we move in (reference dmrg.py:979)."""
+        if self.combine:
+            if self.move_right:
+                theta.itranspose(['(vL.p0)', 'vR'])
+            else:
+                theta.itranspose(['vL', '(p0.vR)'])
+        else:
+            if self.move_right:
+                theta = theta.combine_legs(['vL', 'p0'], qconj=+1, new_axes=0)
+            else:
+                theta = theta.combine_legs(['p0', 'vR'], qconj=-1, new_axes=1)
+        return theta
+
+    def mixed_svd(self, theta):
+        """Reference dmrg.py:998.  Right move: ``theta -- next_B  ==>  U -- S -- VH``; left move:
+        ``next_A -- theta  ==>  U -- S -- VH``; `U` has labels ``'(vL.p)', 'vR'``, `VH` ``'vL', '(p.vR)'``."""
+        mixer = self.mixer
+        move_right = self.move_right
+        update_LP, update_RP = self.update_LP_RP
+        psi = self.psi
+        if move_right:
+            next_B = psi.get_B(self.i0 + 1, form='B').combine_legs(['p', 'vR'], qconj=-1, new_axes=1)
+            if update_RP:
+                assert psi.form[self.i0 + 1] == (0., 1.)
+        else:
+            next_A = psi.get_B(self.i0 - 1, form='A').combine_legs(['vL', 'p'], qconj=+1, new_axes=0)
+            if update_LP:
+                assert psi.form[self.i0 - 1] == (1., 0.)
+        if mixer is None:
+            qtotal = [theta.qtotal, None] if move_right else [None, theta.qtotal]
+            U, S, VH, err, _ = svd_theta(theta, self.trunc_params, qtotal_LR=qtotal, inner_labels=['vR', 'vL'])
+            S_a = S
+            if move_right:   # VH only truncates: VH . next_B is still right-canonical
+                VH = npc.tensordot(VH, next_B, axes=['vR', 'vL'])
+                U.ireplace_label('(vL.p0)', '(vL.p)')
+            else:
+                U = npc.tensordot(next_A, U, axes=['vR', 'vL'])
+                VH.ireplace_label('(p0.vR)', '(p.vR)')
+        elif getattr(mixer, 'can_decompose_1site', False):
+            raise NotImplementedError('one-site mixers (SubspaceExpansion) are not part of this build')
+        else:                # the mixer works on the two-site theta
+            if move_right:
+                next_B.ireplace_label('(p.vR)', '(p1.vR)')
+                theta = npc.tensordot(theta, next_B, axes=['vR', 'vL'])
+                i0 = self.i0
+            else:
+                next_A.ireplace_label('(vL.p)', '(vL.p0)')
+                theta.ireplace_label('(p0.vR)', '(p1.vR)')
+                theta = npc.tensordot(next_A, theta, axes=['vR', 'vL'])
+                i0 = self.i0 - 1
+            qtotal_LR = [psi.get_B(i0, form=None).qtotal, psi.get_B(i0 + 1, form=None).qtotal]
+            U, S, VH, err, S_a = mixer.mixed_svd_2site(engine=self, theta=theta, i0=i0, mix_left=update_LP,
+                                                       mix_right=update_RP, qtotal_LR=qtotal_LR)
+            U.ireplace_label('(vL.p0)', '(vL.p)')
+            VH.ireplace_label('(p1.vR)', '(p.vR)')
+        return U, S, VH, err, S_a

@@ -12,7 +12,120 @@ import numpy as np
 from ..linalg import np_conserved as npc
 from ..linalg.truncation import truncate
 
-__all__ = ['TwoSiteH', 'DensityMatrixMixer']
+__all__ = ['OneSiteH', 'TwoSiteH', 'DensityMatrixMixer']
+
+
+class OneSiteH:
+    r"""Effective Hamiltonian ``LP--W0--RP`` acting on the one-site wave function (reference mps_common.py:1040).
+
+    With ``combine=True`` only the side we move away from is combined: `LHeff` (``'(vR*.p0)', 'wR', '(vR.p0*)'``)
+    for a right move, `RHeff` (``'wL', '(p0*.vL)', '(p0.vL*)'``) for a left move; `theta` then has the labels
+    ``'(vL.p0)', 'vR'`` or ``'vL', '(p0.vR)'``."""
+    length = 1
+    acts_on = ['vL', 'p0', 'vR']
+
+    def __init__(self, env, i0, combine=False, move_right=True, matvec_order=None):
+        self.i0 = i0
+        self.LP = env.get_LP(i0)
+        self.RP = env.get_RP(i0)
+        self.W0 = env.H.get_W(i0).replace_labels(['p', 'p*'], ['p0', 'p0*'])
+        self.dtype = env.H.dtype
+        self.combine = combine
+        self.move_right = move_right
+        self.N = self.LP.get_leg('vR').ind_len * self.W0.get_leg('p0').ind_len * self.RP.get_leg('vL').ind_len
+        if combine:
+            self.combine_Heff(env)
+
+    def matvec(self, theta):
+        """Apply the effective Hamiltonian to `theta` (reference mps_common.py:1118)."""
+        labels = theta.get_leg_labels()
+        if self.combine:
+            if self.move_right:
+                theta = npc.tensordot(self.LHeff, theta, axes=['(vR.p0*)', '(vL.p0)'])     # (vR*.p0) wR vR
+                theta = npc.tensordot(theta, self.RP, axes=[['wR', 'vR'], ['wL', 'vL']])
+                theta.ireplace_labels(['(vR*.p0)', 'vL*'], ['(vL.p0)', 'vR'])
+            else:
+                theta = npc.tensordot(theta, self.RHeff, axes=['(p0.vR)', '(p0*.vL)'])     # vL wL (p0.vL*)
+                theta = npc.tensordot(self.LP, theta, axes=[['vR', 'wR'], ['vL', 'wL']])
+                theta.ireplace_labels(['vR*', '(p0.vL*)'], ['vL', '(p0.vR)'])
+        else:
+            theta = npc.tensordot(self.LP, theta, axes=['vR', 'vL'])
+            theta = npc.tensordot(self.W0, theta, axes=[['wL', 'p0*'], ['wR', 'p0']])
+            theta = npc.tensordot(theta, self.RP, axes=[['wR', 'vR'], ['wL', 'vL']])
+            theta.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
+        theta.itranspose(labels)
+        return theta
+
+    def combine_Heff(self, env):
+        """Reference mps_common.py:1152."""
+        if self.move_right:
+            self.LHeff = env._contract_LHeff(self.i0, 'p0')
+            self.pipeL = self.LHeff.get_leg('(vR*.p0)')
+            self.acts_on = ['(vL.p0)', 'vR']
+        else:
+            self.RHeff = env._contract_RHeff(self.i0, 'p0')
+            self.pipeR = self.RHeff.get_leg('(p0.vL*)')
+            self.acts_on = ['vL', '(p0.vR)']
+
+    def combine_theta(self, theta):
+        """Reference mps_common.py:1173."""
+        if self.combine:
+            if self.move_right:
+                theta = theta.combine_legs(['vL', 'p0'], pipes=self.pipeL)
+            else:
+                theta = theta.combine_legs(['p0', 'vR'], pipes=self.pipeR)
+        return theta.itranspose(self.acts_on)
+
+    def to_matrix(self):
+        """Contract `self` to a 2D Array (reference mps_common.py:1193)."""
+        if self.combine:
+            if self.move_right:
+                contr = npc.tensordot(self.LHeff, self.RP, axes=['wR', 'wL'])
+                contr = contr.combine_legs([['(vR*.p0)', 'vL*'], ['(vR.p0*)', 'vL']], qconj=[+1, -1])
+            else:
+                contr = npc.tensordot(self.LP, self.RHeff, axes=['wR', 'wL'])
+                contr = contr.combine_legs([['vR*', '(p0.vL*)'], ['vR', '(p0*.vL)']], qconj=[+1, -1])
+        else:
+            contr = npc.tensordot(self.LP, self.W0, axes=['wR', 'wL'])
+            contr = npc.tensordot(contr, self.RP, axes=['wR', 'wL'])
+            contr = contr.combine_legs([['vR*', 'p0', 'vL*'], ['vR', 'p0*', 'vL']], qconj=[+1, -1])
+        return contr
+
+    def update_LP(self, env, i, U=None):
+        """Reference mps_common.py:1226."""
+        if self.combine and self.move_right:
+            assert i == self.i0 + 1
+            LP = npc.tensordot(self.LHeff, U, axes=['(vR.p0*)', '(vL.p)'])
+            LP = npc.tensordot(U.conj(), LP, axes=['(vL*.p*)', '(vR*.p0)'])
+            env.set_LP(i, LP, age=env.get_LP_age(i - 1) + 1)
+        else:
+            env.get_LP(i, store=True)
+
+    def update_RP(self, env, i, VH=None):
+        """Reference mps_common.py:1235."""
+        if self.combine and (self.move_right is False):
+            assert i == self.i0 - 1
+            RP = npc.tensordot(VH, self.RHeff, axes=['(p.vR)', '(p0*.vL)'])
+            RP = npc.tensordot(RP, VH.conj(), axes=['(p0.vL*)', '(p*.vR*)'])
+            env.set_RP(i, RP, age=env.get_RP_age(i + 1) + 1)
+        else:
+            env.get_RP(i, store=True)
+
+
+def _get_LHeff(env, i, eff_H):
+    """`LHeff` with ``p0`` labels on site `i`, reusing the one of `eff_H` if it fits (reference :1885)."""
+    if i == eff_H.i0 and hasattr(eff_H, 'LHeff'):
+        return eff_H.LHeff
+    return env._contract_LHeff(i)
+
+
+def _get_RHeff(env, i, eff_H):
+    """`RHeff` with ``p1`` labels on site `i`, reusing the one of `eff_H` if it fits (reference :1893)."""
+    if i == eff_H.i0 + eff_H.length - 1 and hasattr(eff_H, 'RHeff'):
+        if eff_H.length == 1:
+            return eff_H.RHeff.replace_labels(['(p0.vL*)', '(p0*.vL)'], ['(p1.vL*)', '(p1*.vL)'])
+        return eff_H.RHeff
+    return env._contract_RHeff(i)
 
 
 class TwoSiteH:
@@ -176,16 +289,20 @@ class DensityMatrixMixer:
                 should_disable = True
         return None if should_disable else self
 
+    can_decompose_1site = False   # single-site engines fall back to the two-site theta (reference dmrg.py:1088)
+
     def mix_and_decompose_2site(self, engine, theta, i0, mix_left, mix_right, qtotal_LR=[None, None]):
         rho_L, rho_R = self.mix_rho(engine, theta, i0, mix_left, mix_right)
         return self.svd_from_rho(engine, rho_L, rho_R, theta, qtotal_LR)
+
+    mixed_svd_2site = mix_and_decompose_2site     # reference mps_common.py:1938
 
     def mix_rho(self, engine, theta, i0, mix_left, mix_right):
         """Reference mps_common.py:1972."""
         mix_L, mix_R, IdL, IdR, explicit_plus_hc = _mix_LR(engine.env.H, i0, self.amplitude)
         eff_H = engine.eff_H
         if mix_left:
-            LHeff = eff_H.LHeff if hasattr(eff_H, 'LHeff') else engine.env._contract_LHeff(i0)
+            LHeff = _get_LHeff(engine.env, i0, eff_H)
             rho_L = npc.tensordot(LHeff, theta, axes=['(vR.p0*)', '(vL.p0)'])
             rho_L.ireplace_label('(vR*.p0)', '(vL.p0)')
             rho_c = rho_L.conj()
@@ -196,7 +313,7 @@ class DensityMatrixMixer:
         else:
             rho_L = npc.tensordot(theta, theta.conj(), axes=['(p1.vR)', '(p1*.vR*)'])
         if mix_right:
-            RHeff = eff_H.RHeff if hasattr(eff_H, 'RHeff') else engine.env._contract_RHeff(i0 + 1)
+            RHeff = _get_RHeff(engine.env, i0 + 1, eff_H)
             rho_R = npc.tensordot(theta, RHeff, axes=['(p1.vR)', '(p1*.vL)'])
             rho_R.ireplace_label('(p1.vL*)', '(p1.vR)')
             rho_c = rho_R.conj()
