@@ -19,7 +19,7 @@ from ..linalg import np_conserved as npc
 from ..linalg.krylov_based import LanczosGroundState
 from ..linalg.truncation import svd_theta, TruncationError
 from ..networks.mpo import MPOEnvironment
-from .mps_common import OneSiteH, TwoSiteH, DensityMatrixMixer
+from .mps_common import OneSiteH, TwoSiteH, DensityMatrixMixer, SubspaceExpansion
 
 logger = logging.getLogger(__name__)
 
@@ -158,8 +158,13 @@ class TwoSiteDMRGEngine:
         Mixer_class = self.options.get('mixer', False)
         if not Mixer_class:
             return
-        if Mixer_class is True or Mixer_class == 'DensityMatrixMixer':
+        if Mixer_class is True:
             Mixer_class = self.DefaultMixer
+        elif isinstance(Mixer_class, str):
+            known = {'DensityMatrixMixer': DensityMatrixMixer, 'SubspaceExpansion': SubspaceExpansion}
+            if Mixer_class not in known:
+                raise ValueError('unknown mixer ' + repr(Mixer_class))
+            Mixer_class = known[Mixer_class]
         self.mixer = Mixer_class(dict(self.options.get('mixer_params', {})), self.sweeps)
 
     def mixer_deactivate(self):
@@ -490,12 +495,12 @@ class SingleSiteDMRGEngine(TwoSiteDMRGEngine):
     Hamiltonian is :class:`~tenpy_b200.algorithms.mps_common.OneSiteH` (``LP--W0--RP``, dense matvec cost
     ``O(D d chi^3)``), `theta` is split by an SVD whose non-isometric factor is absorbed into the next site.
 
-    Mixers: ``None``, or :class:`DensityMatrixMixer`, which cannot decompose a one-site wave function and therefore
-    works on the two-site `theta` (two-site cost for the mixing step, as the reference warns, dmrg.py:1128).  The
-    reference's default one-site mixer (`SubspaceExpansion`, mps_common.py:2082) is not part of this build; without
-    a mixer the bond dimensions (and charge sectors) of the initial state cannot grow."""
+    Mixers: ``None`` (bond dimensions and charge sectors of the initial state cannot grow), the default
+    :class:`SubspaceExpansion` (one-site cost), or :class:`DensityMatrixMixer`, which cannot decompose a one-site wave
+    function and therefore works on the two-site `theta` (two-site cost for the mixing step, as the reference warns,
+    dmrg.py:1128)."""
     EffectiveH = OneSiteH
-    DefaultMixer = DensityMatrixMixer
+    DefaultMixer = SubspaceExpansion
     n_optimize = 1
 
     def prepare_svd(self, theta):
@@ -538,7 +543,16 @@ class SingleSiteDMRGEngine(TwoSiteDMRGEngine):
                 U = npc.tensordot(next_A, U, axes=['vR', 'vL'])
                 VH.ireplace_label('(p0.vR)', '(p.vR)')
         elif getattr(mixer, 'can_decompose_1site', False):
-            raise NotImplementedError('one-site mixers (SubspaceExpansion) are not part of this build')
+            U, S, VH, err = mixer.mix_and_decompose_1site(engine=self, theta=theta, i0=self.i0, move_right=move_right)
+            S_a = S
+            if move_right:   # `next_B` is the right-canonical B of the MPS; the expanded VH goes into S (2D)
+                S = npc.tensordot(S, VH, axes=['vR', 'vL']) if isinstance(S, npc.Array) else VH.iscale_axis(S, 'vL')
+                VH = next_B
+                U.ireplace_label('(vL.p0)', '(vL.p)')
+            else:
+                S = npc.tensordot(U, S, axes=['vR', 'vL']) if isinstance(S, npc.Array) else U.iscale_axis(S, 'vR')
+                U = next_A
+                VH.ireplace_label('(p0.vR)', '(p.vR)')
         else:                # the mixer works on the two-site theta
             if move_right:
                 next_B.ireplace_label('(p.vR)', '(p1.vR)')

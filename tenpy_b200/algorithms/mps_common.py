@@ -12,7 +12,7 @@ import numpy as np
 from ..linalg import np_conserved as npc
 from ..linalg.truncation import truncate
 
-__all__ = ['OneSiteH', 'TwoSiteH', 'DensityMatrixMixer']
+__all__ = ['OneSiteH', 'TwoSiteH', 'Mixer', 'DensityMatrixMixer', 'SubspaceExpansion']
 
 
 class OneSiteH:
@@ -266,10 +266,12 @@ def _mix_LR(H, i0, amplitude):
     return mix_L, mix_R, IdL, IdR, H.explicit_plus_hc
 
 
-class DensityMatrixMixer:
-    """Mixer perturbing the reduced density matrices with the MPO (reference mps_common.py:1903).
+class Mixer:
+    """Base class of the mixers (reference mps_common.py:1560): a perturbation of the wave function that lets the
+    bond dimension / charge sectors of a bond grow, with an amplitude decaying from sweep to sweep.
 
-    Options `amplitude` (1e-5), `decay` (2.), `disable_after` (15) as the reference's `Mixer` (:1560)."""
+    Options `amplitude` (1e-5), `decay` (2.), `disable_after` (15)."""
+    can_decompose_1site = False
 
     def __init__(self, options, sweep_activated=0):
         options = dict(options or {})
@@ -289,13 +291,134 @@ class DensityMatrixMixer:
                 should_disable = True
         return None if should_disable else self
 
+    def mixed_svd_2site(self, engine, theta, i0, mix_left, mix_right, qtotal_LR=None):
+        raise NotImplementedError('{0} does not implement mixed_svd_2site'.format(type(self).__name__))
+
+    def mix_and_decompose_1site(self, engine, theta, i0, move_right):
+        raise NotImplementedError('{0} does not implement mix_and_decompose_1site'.format(type(self).__name__))
+
+    def mix_and_decompose_2site(self, engine, theta, i0, mix_left, mix_right, qtotal_LR=None):
+        """``theta -> U, S, VH`` with only the mixed side(s) guaranteed isometric (reference mps_common.py:1754):
+        `mixed_svd_2site` if the mixer has it, else built from `mix_and_decompose_1site`."""
+        try:
+            return self.mixed_svd_2site(engine, theta, i0, mix_left, mix_right, qtotal_LR)
+        except NotImplementedError:
+            pass
+        if mix_left and mix_right:
+            qtotal_L, qtotal_R = self.determine_qtotal_L_R(theta.qtotal, qtotal_LR)
+            theta_L = theta.replace_label('(p1.vR)', 'vR')
+            U, _, _, err_L = self.mix_and_decompose_1site(engine, theta_L, i0, move_right=True)
+            U = U.gauge_total_charge(1, qtotal_L)
+            theta_R = theta.replace_labels(['(vL.p0)', '(p1.vR)'], ['vL', '(p0.vR)'])
+            _, S_approx, VH, err_R = self.mix_and_decompose_1site(engine, theta_R, i0 + 1, move_right=False)
+            VH = VH.gauge_total_charge(0, qtotal_R)
+            VH.ireplace_label('(p0.vR)', '(p1.vR)')
+            theta = npc.tensordot(U.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)'])
+            theta = npc.tensordot(theta, VH.conj(), axes=['(p1.vR)', '(p1*.vR*)'])
+            theta.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
+            theta = theta / theta.norm()
+            S = theta
+            err = err_L + err_R
+        elif mix_left:
+            theta_L = theta.replace_label('(p1.vR)', 'vR')
+            U, S, VH, err = self.mix_and_decompose_1site(engine, theta_L, i0, move_right=True)
+            VH.ireplace_label('vR', '(p1.vR)')
+            S_approx = S
+        elif mix_right:
+            theta_R = theta.replace_labels(['(vL.p0)', '(p1.vR)'], ['vL', '(p0.vR)'])
+            U, S, VH, err = self.mix_and_decompose_1site(engine, theta_R, i0 + 1, move_right=False)
+            U.ireplace_label('vL', '(vL.p0)')
+            VH.ireplace_label('(p0.vR)', '(p1.vR)')
+            S_approx = S
+        else:
+            raise ValueError('Expected mix_left=True and/or mix_right=True.')
+        return U, S, VH, err, S_approx
+
+    @staticmethod
+    def determine_qtotal_L_R(theta_qtotal, qtotal_LR):
+        """``qtotal_L + qtotal_R == theta_qtotal`` (reference mps_common.py:1823)."""
+        qtotal_L, qtotal_R = (None, None) if qtotal_LR is None else qtotal_LR
+        if qtotal_L is None and qtotal_R is None:
+            qtotal_L = 0 * theta_qtotal
+            qtotal_R = theta_qtotal
+        elif qtotal_L is None:
+            qtotal_L = theta_qtotal - qtotal_R
+        elif qtotal_R is None:
+            qtotal_R = theta_qtotal - qtotal_L
+        return qtotal_L, qtotal_R
+
+
+class SubspaceExpansion(Mixer):
+    """Direct subspace expansion of a one-site wave function (reference mps_common.py:2082, Hubig et al. 2015): for a
+    right move ``theta_expand[(vL.p0), (wR.vR)] = mix_L[wR] LHeff . theta`` is decomposed instead of `theta`; `U`
+    spans the expanded space, projecting `VH` back onto ``wR = IdL`` recovers `theta` (up to truncation).  Works on
+    one-site wave functions, so single-site DMRG keeps its one-site cost; two-site engines use it through
+    :meth:`Mixer.mix_and_decompose_2site`."""
+    can_decompose_1site = True
+
+    def mix_and_decompose_1site(self, engine, theta, i0, move_right):
+        from ..linalg.truncation import svd_theta
+        bond = i0 if move_right else i0 - 1
+        mix_L, mix_R, IdL, IdR, explicit_plus_hc = _mix_LR(engine.env.H, bond, np.sqrt(self.amplitude))
+        if explicit_plus_hc:
+            raise NotImplementedError('explicit_plus_hc MPOs')
+        if move_right:
+            LHeff = _get_LHeff(engine.env, i0, engine.eff_H).transpose(['(vR*.p0)', 'wR', '(vR.p0*)'])
+            if IdL is not None:
+                theta_expand = npc.tensordot(LHeff.scale_axis(mix_L, 'wR'), theta, axes=['(vR.p0*)', '(vL.p0)'])
+                theta_expand.ireplace_label('(vR*.p0)', '(vL.p0)')
+            else:
+                wR = LHeff.get_leg('wR')
+                stack = [theta.add_trivial_leg(1, 'wR', wR.qconj)]
+                proj = np.ones(wR.ind_len, dtype=bool)
+                if IdR is not None:
+                    proj[IdR] = False
+                LHeff = LHeff.copy(deep=True)
+                LHeff.iproject(proj, 'wR')
+                LHeff = LHeff * np.sqrt(self.amplitude)
+                th = npc.tensordot(LHeff, theta, axes=['(vR.p0*)', '(vL.p0)'])
+                stack.append(th.ireplace_label('(vR*.p0)', '(vL.p0)'))
+                theta_expand = npc.concatenate(stack, axis='wR')
+                IdL = 0
+            theta_expand = theta_expand.combine_legs(['wR', 'vR'], qconj=-1)
+            U, S, VH, err, _ = svd_theta(theta_expand, engine.trunc_params, qtotal_LR=[theta.qtotal, None],
+                                         inner_labels=['vR', 'vL'])
+            VH = VH.split_legs('(wR.vR)').take_slice(IdL, 'wR')      # back to the original theta
+        else:
+            RHeff = _get_RHeff(engine.env, i0, engine.eff_H).transpose(['(p1*.vL)', 'wL', '(p1.vL*)'])
+            if IdR is not None:
+                theta_expand = npc.tensordot(theta, RHeff.scale_axis(mix_R, 'wL'), axes=['(p0.vR)', '(p1*.vL)'])
+                theta_expand.ireplace_label('(p1.vL*)', '(p0.vR)')
+            else:
+                wL = RHeff.get_leg('wL')
+                stack = [theta.add_trivial_leg(1, 'wL', wL.qconj)]
+                proj = np.ones(wL.ind_len, dtype=bool)
+                if IdL is not None:
+                    proj[IdL] = False
+                RHeff = RHeff.copy(deep=True)
+                RHeff.iproject(proj, 'wL')
+                RHeff = RHeff * np.sqrt(self.amplitude)
+                th = npc.tensordot(theta, RHeff, axes=['(p0.vR)', '(p1*.vL)'])
+                stack.append(th.ireplace_label('(p1.vL*)', '(p0.vR)'))
+                theta_expand = npc.concatenate(stack, axis='wL')
+                IdR = 0
+            theta_expand = theta_expand.combine_legs(['vL', 'wL'], qconj=+1)
+            U, S, VH, err, _ = svd_theta(theta_expand, engine.trunc_params, qtotal_LR=[None, theta.qtotal],
+                                         inner_labels=['vR', 'vL'])
+            U = U.split_legs('(vL.wL)').take_slice(IdR, 'wL')
+        return U, S, VH, err
+
+
+class DensityMatrixMixer(Mixer):
+    """Mixer perturbing the reduced density matrices with the MPO (reference mps_common.py:1903).
+
+    Options `amplitude` (1e-5), `decay` (2.), `disable_after` (15) as the reference's `Mixer` (:1560)."""
     can_decompose_1site = False   # single-site engines fall back to the two-site theta (reference dmrg.py:1088)
 
-    def mix_and_decompose_2site(self, engine, theta, i0, mix_left, mix_right, qtotal_LR=[None, None]):
+    def mixed_svd_2site(self, engine, theta, i0, mix_left, mix_right, qtotal_LR=[None, None]):
+        """Reference mps_common.py:1938."""
         rho_L, rho_R = self.mix_rho(engine, theta, i0, mix_left, mix_right)
         return self.svd_from_rho(engine, rho_L, rho_R, theta, qtotal_LR)
-
-    mixed_svd_2site = mix_and_decompose_2site     # reference mps_common.py:1938
 
     def mix_rho(self, engine, theta, i0, mix_left, mix_right):
         """Reference mps_common.py:1972."""

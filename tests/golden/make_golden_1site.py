@@ -84,6 +84,30 @@ def main():
     out['ref_E1'] = np.float64(E)
     out['ref_S1'] = psi.entanglement_entropy()
     print('refine', out['ref_E2'], E)
+    # (4) SubspaceExpansion mixer (the reference's default for single-site DMRG): single-site TFI / XXZ-Sz from product
+    #     states, and the two-site engine using it through Mixer.mix_and_decompose_2site
+    mp = {'amplitude': 1e-3, 'decay': 2., 'disable_after': 8}
+    L = 12
+    M = TFIChain(dict(L=L, J=1., g=1.1, bc_MPS='finite', conserve=None))
+    psi = MPS.from_product_state(M.lat.mps_sites(), ['up'] * L, bc='finite')
+    eng = dmrg.SingleSiteDMRGEngine(psi, M, {'mixer': True, 'mixer_params': dict(mp), 'max_E_err': 1e-11,
+                                             'max_S_err': 1e-8, 'trunc_params': {'chi_max': 24, 'svd_min': 1e-10},
+                                             'combine': True, 'max_sweeps': 24})
+    assert type(eng.mixer).__name__ == 'SubspaceExpansion' or eng.mixer is None
+    E, _ = eng.run()
+    out['se_tfi_E'], out['se_tfi_S'], out['se_tfi_chi'] = np.float64(E), psi.entanglement_entropy(), np.array(psi.chi)
+    print('se_tfi', E, eng.sweeps, psi.chi)
+    L = 10
+    M = SpinChain(dict(L=L, S=0.5, Jx=1., Jy=1., Jz=0.8, bc_MPS='finite', conserve='Sz'))
+    for key, Engine, combine in (('se_xxz1', dmrg.SingleSiteDMRGEngine, True), ('se_xxz1n', dmrg.SingleSiteDMRGEngine, False),
+                                 ('se_xxz2', dmrg.TwoSiteDMRGEngine, True)):
+        psi = MPS.from_product_state(M.lat.mps_sites(), ['up', 'down'] * (L // 2), bc='finite')
+        eng = Engine(psi, M, {'mixer': 'SubspaceExpansion', 'mixer_params': dict(mp), 'max_E_err': 1e-11,
+                              'max_S_err': 1e-8, 'trunc_params': {'chi_max': 32, 'svd_min': 1e-10},
+                              'combine': combine, 'max_sweeps': 24})
+        E, _ = eng.run()
+        out[key + '_E'], out[key + '_S'], out[key + '_chi'] = np.float64(E), psi.entanglement_entropy(), np.array(psi.chi)
+        print(key, E, eng.sweeps, psi.chi)
     np.savez_compressed(os.path.join(HERE, 'dmrg_1site.npz'), **out)
 
 

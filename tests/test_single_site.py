@@ -93,6 +93,49 @@ def _check_engine():
     assert np.max(np.abs(psi.entanglement_entropy() - g['ref_S1'])) < 1e-7
 
 
+def _check_subspace_expansion():
+    """the reference's default one-site mixer: single-site engine (combine on / off) and the two-site engine through
+    Mixer.mix_and_decompose_2site, energies / entropies of the reference"""
+    from tenpy_b200.models import TFIChain, SpinChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import SubspaceExpansion
+    g = h.load('dmrg_1site.npz')
+    mp = {'amplitude': 1e-3, 'decay': 2., 'disable_after': 8}
+    L = 12
+    M = TFIChain({'L': L, 'J': 1., 'g': 1.1, 'conserve': None})
+    psi = MPS.from_product_state(M.lat_sites, ['up'] * L)
+    eng = dmrg.SingleSiteDMRGEngine(psi, M, {'mixer': True, 'mixer_params': dict(mp), 'max_E_err': 1e-11,
+                                             'max_S_err': 1e-8, 'trunc_params': {'chi_max': 24, 'svd_min': 1e-10},
+                                             'combine': True, 'max_sweeps': 24})
+    E, _ = eng.run()
+    assert eng.DefaultMixer is SubspaceExpansion
+    assert abs(E - g['se_tfi_E']) < 1e-10 * abs(g['se_tfi_E'])
+    assert np.max(np.abs(psi.entanglement_entropy() - g['se_tfi_S'])) < 1e-7
+    assert np.max(psi.isometry_test()) < 1e-11
+    L = 10
+    M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 0.8, 'conserve': 'Sz'})
+    for key, Engine, combine in (('se_xxz1', dmrg.SingleSiteDMRGEngine, True), ('se_xxz1n', dmrg.SingleSiteDMRGEngine, False),
+                                 ('se_xxz2', dmrg.TwoSiteDMRGEngine, True)):
+        psi = MPS.from_product_state(M.lat_sites, ['up', 'down'] * (L // 2))
+        eng = Engine(psi, M, {'mixer': 'SubspaceExpansion', 'mixer_params': dict(mp), 'max_E_err': 1e-11,
+                              'max_S_err': 1e-8, 'trunc_params': {'chi_max': 32, 'svd_min': 1e-10},
+                              'combine': combine, 'max_sweeps': 24})
+        E, _ = eng.run()
+        assert abs(E - g[key + '_E']) < 1e-10 * abs(g[key + '_E']), key
+        assert np.max(np.abs(psi.entanglement_entropy() - g[key + '_S'])) < 1e-7, key
+        assert list(psi.chi) == list(g[key + '_chi']), key
+
+
+def test_subspace_expansion_host_logic(fake_device):
+    _check_subspace_expansion()
+
+
+@pytest.mark.gpu
+def test_subspace_expansion_gpu(gpu_lib):
+    _check_subspace_expansion()
+
+
 def test_onesite_matvec_host_logic(fake_device):
     _check_matvec()
     _check_onesite_H_consistency()
