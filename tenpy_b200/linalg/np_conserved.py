@@ -30,7 +30,7 @@ from .. import backend
 
 __all__ = ['QTYPE', 'ChargeInfo', 'LegCharge', 'LegPipe', 'Array', 'zeros', 'eye_like', 'diag', 'tensordot',
            'inner', 'norm', 'svd', 'eigh', 'eigvalsh', 'outer', 'trace', 'to_iterable_arrays', 'pinv', 'concatenate_qdata',
-           'concatenate', 'ones', 'detect_qtotal']
+           'concatenate', 'ones', 'detect_qtotal', 'qr']
 
 _PLAN_CACHE = {}
 svd_stats = {'calls': 0, 'jacobi_sweeps': []}   # diagnostics: Jacobi sweeps used by each npc.svd call
@@ -1451,6 +1451,139 @@ def _fill_null_vectors(lib, m, n, k, r, kf, transposed, bufU, u_off, bufV, v_off
             _strided_copy(lib, bufU, u_off, V, 0, [r, m], [1, k], [m, 1])
         X = _null_space_completion(lib, V, r, m, kf)
         _strided_copy(lib, X, 0, bufU, u_off + r, [kf, m], [m, 1], [1, k])
+
+
+qr_stats = {'calls': 0, 'columns': 0, 'replaced': 0}   # diagnostics of the Gram-Schmidt QR
+
+
+def _block_qr_cgs2(lib, m, n, A, Q, R):
+    """``A (m x n) = Q (m x k) R (k x n)``, ``k = min(m, n)``, on device buffers (row-major views): classical
+    Gram-Schmidt with re-orthogonalisation ("twice is enough"), column by column, built from the existing kernels --
+    two skinny GEMMs per pass (projection on the previous vectors), one dot + one scal per column -- and
+    ``R = Q^T A`` by one GEMM with the strictly lower triangle dropped.  A column that is linearly dependent on the
+    previous ones (norm after projection below ``64 eps`` of its original norm) is replaced by an orthonormalised unit
+    vector, so that `Q` stays an isometry (LAPACK's Householder QR returns an orthonormal completion there, too).
+
+    Cost model: one host round trip per column (the norm).  This is a functional stand-in on the cold paths
+    (`MPS.canonical_form`); a batched Householder kernel is round-2 work."""
+    k = min(m, n)
+    out = backend.scalar_out()
+    scratch = backend.dot_scratch()
+    T = backend.empty(n * m)                                   # T = A^T: row j = column j of A (contiguous)
+    _strided_copy(lib, A, 0, T, 0, [n, m], [1, n], [m, 1])
+    cn = backend.empty(n)
+    lib.col_sqnorms(m, n, n, A, cn)
+    col_norm = np.sqrt(backend.to_host(cn))
+    Qt = backend.zeros(k * m)
+    w = backend.empty(max(k, 1))
+    tmp = backend.empty(m)
+    ones = backend.to_device(np.ones(1))
+    next_unit = 0
+    for j in range(k):
+        v = T[j * m:(j + 1) * m].clone()
+        replaced = False
+        while True:
+            for _ in range(2):
+                if j > 0:
+                    _gemm(lib, j, 1, m, Qt[:j * m], v, w[:j])          # w = Q_{<j}^T v
+                    _gemm(lib, 1, m, j, w[:j], Qt[:j * m], tmp)        # tmp = w^T Q_{<j}^T
+                    lib.axpy(m, -1., tmp, v)
+            lib.dot(m, v, v, scratch, out)
+            nrm = float(np.sqrt(max(backend.read_scalar(out), 0.)))
+            ref = 1. if replaced else col_norm[j]
+            if nrm > 64 * np.finfo(np.float64).eps * ref and nrm > 0.:
+                break
+            # dependent column: continue with a unit vector (the next one not yet tried)
+            if next_unit >= m:
+                raise RuntimeError('QR: could not complete the isometry')
+            v = backend.zeros(m)
+            seg = np.array([[0, next_unit, 1]], dtype=np.int64)
+            lib.axpy_segments(1, backend.to_device(seg), 1, 1., ones, v)
+            next_unit += 1
+            replaced = True
+            qr_stats['replaced'] += 1
+        lib.scal(m, 1. / nrm, v)
+        Qt[j * m:(j + 1) * m].copy_(v)
+    qr_stats['columns'] += k
+    _strided_copy(lib, Qt, 0, Q, 0, [m, k], [1, m], [k, 1])
+    Rfull = backend.empty(k * n)
+    _gemm(lib, k, n, m, Qt, A, Rfull)
+    rec = np.zeros((k, 22), dtype=np.int64)                        # row i of R: entries i .. n-1
+    i = np.arange(k, dtype=np.int64)
+    rec[:, 0] = rec[:, 1] = i * n + i
+    rec[:, 2] = n - i
+    rec[:, 3] = 1
+    rec[:, 4:10] = 1
+    rec[:, 4] = n - i
+    rec[:, 10] = rec[:, 16] = 1
+    lib.copy_blocks(rec, backend.to_device(rec), Rfull, R)
+
+
+def qr(a, mode='reduced', inner_labels=[None, None], cutoff=None, pos_diag_R=False, qtotal_Q=None, inner_qconj=+1):
+    """Q-R decomposition ``a == tensordot(Q, R, axes=1)`` per charge block (reference npc:4139): `Q` an isometry with
+    legs ``(a.legs[0], inner.conj())``, `R` upper triangular with legs ``(inner, a.legs[1])``.
+
+    Only ``mode='reduced'`` and ``cutoff=None``.  The diagonal of `R` is positive by construction (Gram-Schmidt, see
+    :func:`_block_qr_cgs2`), i.e. the result is the unique decomposition the reference returns for
+    ``pos_diag_R=True`` (for full-rank blocks)."""
+    if a.rank != 2:
+        raise ValueError('expect a matrix!')
+    if mode != 'reduced':
+        raise NotImplementedError("qr: only mode='reduced'")
+    if cutoff is not None:
+        raise NotImplementedError('qr with cutoff (pivoted QR discarding dependent columns)')
+    a_labels = a._labels
+    label_Q, label_R = inner_labels
+    piped_axes, a = a.as_completely_blocked()
+    chinfo = a.chinfo
+    lay = a._layout
+    a_leg0 = a.legs[0]
+    m, n = lay.shapes[:, 0], lay.shapes[:, 1]
+    k = np.minimum(m, n)
+    # the new inner leg = the row sectors that have a block, truncated to k (reference npc:4190-4215)
+    mask = np.zeros(a_leg0.ind_len, dtype=np.bool_)
+    for q1, kk in zip(lay.qdata[:, 0], k):
+        i0 = int(a_leg0.slices[q1])
+        mask[i0:i0 + int(kk)] = True
+    inner_leg = a_leg0.to_LegCharge() if isinstance(a_leg0, LegPipe) else a_leg0.copy()
+    map_qind, _, inner_leg = inner_leg.project(mask)
+    charges_in = inner_leg.charges
+    if qtotal_Q is not None:
+        qtotal_Q = chinfo.make_valid(qtotal_Q)
+        charges_in = chinfo.make_valid(charges_in - inner_leg.qconj * qtotal_Q)
+    qc = inner_leg.qconj
+    if qc != inner_qconj:
+        charges_in = chinfo.make_valid(-charges_in)
+        qc = inner_qconj
+    inner_leg = LegCharge.from_qind(chinfo, inner_leg.slices, charges_in, qc)
+    Q = Array([a_leg0, inner_leg.conj()], np.float64, qtotal_Q)
+    R = Array([inner_leg, a.legs[1]], np.float64, chinfo.make_valid(a.qtotal - Q.qtotal))
+    if lay.nblocks:
+        qi_C = map_qind[lay.qdata[:, 0]].astype(np.int64)
+        lay_Q, perm_Q = BlockLayout.from_legs(Q.legs, np.stack([lay.qdata[:, 0], qi_C], axis=1))
+        lay_R, perm_R = BlockLayout.from_legs(R.legs, np.stack([qi_C, lay.qdata[:, 1]], axis=1))
+        q_off = np.empty(lay.nblocks, dtype=np.int64)
+        r_off = np.empty(lay.nblocks, dtype=np.int64)
+        q_off[perm_Q] = lay_Q.offsets
+        r_off[perm_R] = lay_R.offsets
+        bufQ = backend.zeros(lay_Q.size)
+        bufR = backend.zeros(lay_R.size)
+        lib = backend.get_lib()
+        for b in range(lay.nblocks):
+            mb, nb, kb = int(m[b]), int(n[b]), int(k[b])
+            ao = int(lay.offsets[b])
+            _block_qr_cgs2(lib, mb, nb, a._buf[ao:ao + mb * nb], bufQ[int(q_off[b]):int(q_off[b]) + mb * kb],
+                           bufR[int(r_off[b]):int(r_off[b]) + kb * nb])
+        Q._set_blocks(lay_Q, bufQ)
+        R._set_blocks(lay_R, bufR)
+        qr_stats['calls'] += 1
+    if 0 in piped_axes:
+        Q = Q.split_legs(0)
+    if 1 in piped_axes:
+        R = R.split_legs(-1)
+    Q.iset_leg_labels([a_labels[0], label_Q])
+    R.iset_leg_labels([label_R, a_labels[1]])
+    return Q, R
 
 
 def pinv(a, cutoff=1.e-15):

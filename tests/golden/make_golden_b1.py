@@ -57,6 +57,19 @@ def main():
         mg.dump_array('c%d_b' % case, b, out)
         mg.dump_array('c%d_c' % case, c, out)
         mg.dump_array('c%d_cat' % case, npc.concatenate([a, b, c], axis='b'), out)
+        # qr with the unique sign convention (pos_diag_R), default inner leg and with qtotal_Q / inner_qconj=-1
+        mleg0, mleg1 = mg.rand_leg(rng, chinfo, 9, +1), mg.rand_leg(rng, chinfo, 8, -1)
+        mat = mg.rand_array(rng, [mleg0, mleg1], labels=['x', 'y'])
+        mg.dump_array('c%d_qr_m' % case, mat, out)
+        Q, R = npc.qr(mat, inner_labels=['q', 'r'], pos_diag_R=True)
+        mg.dump_array('c%d_qr_Q' % case, Q, out)
+        mg.dump_array('c%d_qr_R' % case, R, out)
+        tall = mat.combine_legs(['x'])          # a piped first leg
+        matq = mg.rand_array(rng, [mleg0, mleg1], qtotal=mleg0.get_charge(0) + mleg1.get_charge(0), labels=['x', 'y'])
+        mg.dump_array('c%d_qr_mq' % case, matq, out)
+        Q, R = npc.qr(matq, inner_labels=['q', 'r'], pos_diag_R=True, qtotal_Q=matq.qtotal, inner_qconj=-1)
+        mg.dump_array('c%d_qr_Qq' % case, Q, out)
+        mg.dump_array('c%d_qr_Rq' % case, R, out)
         case += 1
     out['n_cases'] = np.int64(case)
     np.savez_compressed(os.path.join(HERE, 'b1_ops.npz'), **out)

@@ -57,6 +57,47 @@ def _check_b1_ops():
         assert np.array_equal(npc.detect_qtotal(a.to_ndarray(), a.legs), a.qtotal)
 
 
+def _check_qr():
+    """npc.qr per charge block against the reference's QR with pos_diag_R=True (unique for full-rank blocks): legs and
+    block tables exact, entries to 1e-12; plus Q isometric, R upper triangular, Q R = A for ragged / deficient input"""
+    from tenpy_b200.linalg import np_conserved as npc
+    g = h.load('b1_ops.npz')
+    for case in range(int(g['n_cases'])):
+        pre = 'c%d_' % case
+        for key, kw in (('', {}), ('q', None)):
+            mat = h.to_product(h.oarray_from(g, pre + 'qr_m' + key))
+            if kw is None:
+                kw = dict(qtotal_Q=mat.qtotal, inner_qconj=-1)
+            Q, R = npc.qr(mat, inner_labels=['q', 'r'], pos_diag_R=True, **kw)
+            h.assert_close(h.to_oracle(Q), h.oarray_from(g, pre + 'qr_Q' + key), 1e-12)
+            h.assert_close(h.to_oracle(R), h.oarray_from(g, pre + 'qr_R' + key), 1e-12)
+            assert npc.norm(npc.tensordot(Q, R, axes=1) - mat) < 1e-13 * npc.norm(mat)
+    rng = np.random.default_rng(7)
+    for shape in [(7, 4), (4, 7), (1, 3), (3, 1), (33, 20)]:
+        A = rng.standard_normal(shape)
+        Q, R = npc.qr(npc.Array.from_ndarray_trivial(A))
+        q, r = Q.to_ndarray(), R.to_ndarray()
+        kk = min(shape)
+        assert np.max(np.abs(q @ r - A)) < 1e-13 * np.abs(A).max() * max(shape)
+        assert np.max(np.abs(q.T @ q - np.eye(kk))) < 1e-13
+        assert np.all(np.tril(r, -1) == 0.) and np.all(np.diag(r) > 0.)
+    A = rng.standard_normal((12, 3)) @ rng.standard_normal((3, 8))            # rank 3: dependent columns are replaced
+    Q, R = npc.qr(npc.Array.from_ndarray_trivial(A))
+    q, r = Q.to_ndarray(), R.to_ndarray()
+    assert np.max(np.abs(q @ r - A)) < 1e-13 * np.abs(A).max() * 12 and np.max(np.abs(q.T @ q - np.eye(8))) < 1e-13
+    with pytest.raises(NotImplementedError):
+        npc.qr(npc.Array.from_ndarray_trivial(A), mode='complete')
+
+
+def test_qr_host_logic(fake_device):
+    _check_qr()
+
+
+@pytest.mark.gpu
+def test_qr_gpu(gpu_lib):
+    _check_qr()
+
+
 def test_b1_ops_host_logic(fake_device):
     _check_b1_ops()
 
