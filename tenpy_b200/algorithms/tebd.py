@@ -15,9 +15,9 @@ import numpy as np
 import scipy.linalg
 
 from ..linalg import np_conserved as npc
-from ..linalg.truncation import svd_theta, TruncationError
+from ..linalg.truncation import svd_theta, TruncationError, decompose_theta_qr_based
 
-__all__ = ['TEBDEngine']
+__all__ = ['TEBDEngine', 'QRBasedTEBDEngine']
 
 
 class TEBDEngine:
@@ -223,3 +223,78 @@ class TEBDEngine:
                 DeltaE = abs(Eold - E)
                 Eold = E
         return Eold
+
+
+class QRBasedTEBDEngine(TEBDEngine):
+    """TEBD with the QR based truncation of :func:`~tenpy_b200.linalg.truncation.decompose_theta_qr_based` instead of the
+    SVD of the full two-site wave function (reference tebd.py:619, arXiv:2212.09782): only the small bond matrix is
+    decomposed.  Options as the reference: `cbe_expand` (0.1), `cbe_expand_0`, `cbe_min_block_increase` (1),
+    `use_eig_based_svd` (False), `compute_err` (True)."""
+
+    def _expansion_rate(self, i):
+        """Reference tebd.py:669."""
+        expand = self.options.get('cbe_expand', 0.1)
+        expand_0 = self.options.get('cbe_expand_0', None)
+        if expand_0 is None or expand_0 == expand:
+            return expand
+        chi_max = self.trunc_params.get('chi_max', None)
+        if chi_max is None:
+            raise ValueError('Need to specify trunc_params["chi_max"] in order to use cbe_expand_0.')
+        chi = min(np.shape(self.psi.get_SL(i)))
+        return max(expand_0 - chi / chi_max * (expand_0 - expand), expand)
+
+    def update_bond(self, i, U_bond):
+        """Reference tebd.py:681."""
+        i0, i1 = i - 1, i
+        expand = self._expansion_rate(i)
+        C = self.psi.get_theta(i0, n=2, formL=0.)
+        C = npc.tensordot(U_bond, C, axes=(['p0*', 'p1*'], ['p0', 'p1']))
+        C.itranspose(['vL', 'p0', 'p1', 'vR'])
+        theta = C.scale_axis(self.psi.get_SL(i0), 'vL')
+        theta = theta.combine_legs([('vL', 'p0'), ('p1', 'vR')], qconj=[+1, -1])
+        old_B_L = self.psi.get_B(i0, 'B')
+        old_B_R = self.psi.get_B(i1, 'B')
+        _, S, B_R, form, trunc_err, renormalize = decompose_theta_qr_based(
+            old_qtotal_L=old_B_L.qtotal, old_qtotal_R=old_B_R.qtotal, old_bond_leg=old_B_R.get_leg('vL'), theta=theta,
+            move_right=False, expand=expand, min_block_increase=self.options.get('cbe_min_block_increase', 1),
+            use_eig_based_svd=self.options.get('use_eig_based_svd', False), trunc_params=self.trunc_params,
+            compute_err=self.options.get('compute_err', True), return_both_T=False)
+        assert form[1] == 'B'
+        B_L = npc.tensordot(C.combine_legs(('p1', 'vR'), pipes=theta.legs[1]), B_R.conj(),
+                            axes=['(p1.vR)', '(p*.vR*)'])
+        B_L = B_L / renormalize
+        B_L.ireplace_labels(['p0', 'vL*'], ['p', 'vR'])
+        B_R = B_R.split_legs(1)
+        self.psi.norm *= renormalize
+        self.psi.set_B(i0, B_L, form='B')
+        self.psi.set_SL(i1, S)
+        self.psi.set_B(i1, B_R, form='B')
+        self._trunc_err_bonds[i] = self._trunc_err_bonds[i] + trunc_err
+        return trunc_err
+
+    def update_bond_imag(self, i, U_bond):
+        """Reference tebd.py:741."""
+        i0, i1 = i - 1, i
+        expand = self._expansion_rate(i)
+        theta = self.psi.get_theta(i0, n=2)
+        theta = npc.tensordot(U_bond, theta, axes=(['p0*', 'p1*'], ['p0', 'p1']))
+        theta.itranspose(['vL', 'p0', 'p1', 'vR'])
+        theta = theta.combine_legs([('vL', 'p0'), ('p1', 'vR')], qconj=[+1, -1])
+        old_B_L = self.psi.get_B(i0, 'B')
+        old_B_R = self.psi.get_B(i1, 'B')
+        if self.options.get('use_eig_based_svd', False):
+            raise NotImplementedError('update_bond_imag does not (yet) support eig based SVD')
+        A_L, S, B_R, form, trunc_err, renormalize = decompose_theta_qr_based(
+            old_qtotal_L=old_B_L.qtotal, old_qtotal_R=old_B_R.qtotal, old_bond_leg=old_B_R.get_leg('vL'), theta=theta,
+            move_right=False, expand=expand, min_block_increase=self.options.get('cbe_min_block_increase', 1),
+            use_eig_based_svd=False, trunc_params=self.trunc_params,
+            compute_err=self.options.get('compute_err', True), return_both_T=True)
+        assert form == ['A', 'B']
+        A_L = A_L.split_legs(0)
+        B_R = B_R.split_legs(1)
+        self.psi.norm *= renormalize
+        self.psi.set_B(i0, A_L, form='A')
+        self.psi.set_SL(i1, S)
+        self.psi.set_B(i1, B_R, form='B')
+        self._trunc_err_bonds[i] = self._trunc_err_bonds[i] + trunc_err
+        return trunc_err

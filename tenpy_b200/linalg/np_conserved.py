@@ -1611,6 +1611,7 @@ def eigh(a, UPLO='L', sort=None):
     a.legs[0].test_contractible(a.legs[1])
     if np.any(a.qtotal != a.chinfo.make_valid()):
         raise ValueError('Non-trivial qtotal -> Nilpotent. Not diagonizable!?')
+    a_label0 = a._labels[0]
     piped_axes, a = a.as_completely_blocked()
     leg = a.legs[0]
     lay = a._layout
@@ -1642,15 +1643,31 @@ def eigh(a, UPLO='L', sort=None):
         bufW = backend.empty(int(w_off[-1]))
         lib.block_eigh(nn, lay.offsets, w_off[:-1], lay_V.offsets[stored], a._buf, bufW, bufV)
         w = backend.to_host(bufW)
-        perms = None
+        recs, pool, at = [], [], 0
         for j, qi in enumerate(stored):
             rw = w[w_off[j]:w_off[j + 1]]
-            if sort is not None and sort != 'm<' and sort != '<':
-                raise NotImplementedError('eigh(sort=...) other than ascending')
+            if sort is not None and sort != '<':
+                # order inside the block as requested (reference tools/misc.py argsort): permute the eigenvalues
+                # on the host and the columns of V with one take launch
+                key = {'m<': np.abs(rw), 'm>': -np.abs(rw), '>': -rw}.get(sort)
+                if key is None:
+                    raise ValueError('unknown sort option ' + repr(sort))
+                perm = np.argsort(key, kind='stable')
+                if np.any(perm != np.arange(len(perm))):
+                    nq = len(rw)
+                    recs.append([int(lay_V.offsets[qi]), int(lay_V.offsets[qi]), nq, nq, 1, nq, at])
+                    pool.append(perm.astype(np.int64))
+                    at += nq
+                    rw = rw[perm]
             resw[leg.get_slice(qi)] = rw
+        if recs:
+            rec = np.array(recs, dtype=np.int64)
+            src = bufV.clone()
+            lib.take_blocks(rec, backend.to_device(rec), backend.to_device(np.concatenate(pool)), src, bufV)
     V._set_blocks(lay_V, bufV)
     if len(piped_axes) > 0:
         V = V.split_legs(0)
+    V.iset_leg_labels([a_label0, 'eig'] if a_label0 != 'eig' else [None, 'eig'])
     return resw, V
 
 

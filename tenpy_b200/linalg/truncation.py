@@ -12,7 +12,7 @@ import numpy as np
 
 from . import np_conserved as npc
 
-__all__ = ['TruncationError', 'truncate', 'svd_theta']
+__all__ = ['TruncationError', 'truncate', 'svd_theta', 'decompose_theta_qr_based']
 
 
 class TruncationError:
@@ -214,3 +214,171 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
     U.iproject(piv, axes=1)
     VH.iproject(piv, axes=0)
     return U, S, VH, err, renormalization
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# QR based truncation (reference truncation.py:370-713)
+def _block_vector_norms(arr, norm_axis):
+    """per stored block of the 2D Array `arr`: 2-norms over `norm_axis` (host vectors, layout order) -- the reference
+    reads ``np.linalg.norm(block, axis=norm_axis)`` from its host blocks (truncation.py:456); here one squared-norm
+    launch per block and a D2H copy of the resulting vectors."""
+    from .. import backend
+    src = arr if norm_axis == 0 else arr.transpose([1, 0])
+    lay = src._layout
+    lib = backend.get_lib()
+    out = []
+    for o, (mm, nn) in zip(lay.offsets, lay.shapes):
+        mm, nn = int(mm), int(nn)
+        buf = backend.empty(nn)
+        lib.col_sqnorms(mm, nn, nn, src._buf[int(o):int(o) + mm * nn], buf)
+        out.append(np.sqrt(backend.to_host(buf)))
+    return out, lay.qdata[:, 1]      # qindex (of `arr`) along the axis that is NOT summed over
+
+
+def _qr_theta_Y0(old_qtotal_L, old_qtotal_R, old_bond_leg, theta, move_right, expand, min_block_increase):
+    """Initial guess `Y0` of the isometry on the expanded bond: the columns (rows) of `theta` with the largest norms in
+    every charge block, ``expand`` times the old bond dimension more than the old leg had (reference truncation.py:370).
+    Returns an Array with legs ``[(vL.p0), vR]`` (`move_right`) or ``[vL, (p1.vR)]``."""
+    assert min_block_increase >= 0
+    assert expand is not None and expand != 0
+    Y0 = theta.copy(deep=False)
+    if move_right:
+        Y0.legs[1] = Y0.legs[1].to_LegCharge()
+        Y0.ireplace_label('(p1.vR)', 'vR')
+        q_axis, norm_axis, lab = 1, 0, 'vR'
+    else:
+        Y0.legs[0] = Y0.legs[0].to_LegCharge()
+        Y0.ireplace_label('(vL.p0)', 'vL')
+        q_axis, norm_axis, lab = 0, 1, 'vL'
+    # (the reference calls `Y0.gauge_total_charge(...)` here without using the returned copy: no effect)
+    v_old = old_bond_leg
+    if not v_old.is_blocked():
+        v_old = v_old.sort()[1]
+    v_new = Y0.get_leg(lab)                   # blocked: created from a pipe
+    piv = np.zeros(v_new.ind_len, dtype=bool)
+    increase_per_block = max(min_block_increase, int(v_old.ind_len * expand // v_new.block_number))
+    sizes_old = v_old.get_block_sizes()
+    sizes_new = v_new.get_block_sizes()
+    norms, qidx = _block_vector_norms(Y0, norm_axis)
+    by_q = {int(q): nv for q, nv in zip(qidx, norms)}
+    j_old = 0
+    q_old = v_old.charges[j_old, :]
+    for j_new, q_new in enumerate(v_new.charges):
+        if np.all(q_new == q_old):            # charge block both in v_new and v_old
+            s_new = sizes_old[j_old] + increase_per_block
+            j_old += 1
+            if j_old < len(v_old.charges):
+                q_old = v_old.charges[j_old, :]
+            else:
+                q_old = None
+        else:
+            s_new = increase_per_block
+        s_new = min(int(s_new), int(sizes_new[j_new]))
+        nv = by_q.get(j_new)
+        if nv is None:                        # block not stored in theta
+            continue
+        kept = np.argsort(-nv, kind='stable')[:s_new]
+        piv[v_new.slices[j_new] + kept] = True
+    Y0.iproject(piv, lab)
+    return Y0
+
+
+def _eig_based_svd(A, need_U=True, need_Vd=True, inner_labels=[None, None], trunc_params=None):
+    """Singular values / one set of singular vectors of `A` from the eigen-decomposition of ``A A^dagger`` or
+    ``A^dagger A`` (reference truncation.py:473): two GEMM-class contractions and a batched `eigh` instead of an SVD."""
+    assert A.rank == 2
+    if need_U and need_Vd:
+        raise NotImplementedError('both U and Vd from eigh: relative phases are not fixed (as in the reference)')
+    U = Vd = None
+    if need_U:
+        L, U = npc.eigh(npc.tensordot(A, A.conj(), axes=[1, 1]), sort='>')
+        U.ireplace_label('eig', inner_labels[0])
+    elif need_Vd:
+        L, V = npc.eigh(npc.tensordot(A.conj(), A, axes=[0, 0]), sort='>')
+        Vd = V.iconj().itranspose().ireplace_label('eig*', inner_labels[1])
+    else:
+        A2 = npc.tensordot(A, A.conj(), axes=[1, 1]) if A.shape[1] >= A.shape[0] else \
+            npc.tensordot(A.conj(), A, axes=[0, 0])
+        L = npc.eigvalsh(A2)
+    S = np.sqrt(np.abs(L))
+    if trunc_params is not None:
+        piv, renormalize, trunc_err = truncate(S, trunc_params)
+        S = S[piv] / renormalize
+        if need_U:
+            U.iproject(piv, 1)
+        if need_Vd:
+            Vd.iproject(piv, 0)
+    else:
+        renormalize = np.linalg.norm(S)
+        S = S / renormalize
+        trunc_err = TruncationError()
+    return U, S, Vd, trunc_err, renormalize
+
+
+def decompose_theta_qr_based(old_qtotal_L, old_qtotal_R, old_bond_leg, theta, move_right, expand, min_block_increase,
+                             use_eig_based_svd, trunc_params, compute_err, return_both_T):
+    """QR based decomposition and truncation of the two-site wave function ``theta[(vL.p0), (p1.vR)]``
+    (reference truncation.py:533): two QR steps on an expanded bond (controlled bond expansion) reduce `theta` to a
+    small bond matrix ``Xi``, only ``Xi`` is decomposed by an SVD (or `eigh`).
+
+    Returns ``(T_Lc, S, T_Rc, form, trunc_err, renormalization)`` as the reference."""
+    if compute_err:
+        return_both_T = True
+    Y0 = _qr_theta_Y0(old_qtotal_L, old_qtotal_R, old_bond_leg, theta, move_right, expand, min_block_increase)
+    if move_right:
+        theta_i1 = npc.tensordot(Y0.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)']).ireplace_label('vR*', 'vL')
+        theta_i1.itranspose(['(p1.vR)', 'vL'])
+        B_R, _ = npc.qr(theta_i1, inner_labels=['vL', 'vR'], inner_qconj=-1)
+        B_R.itranspose(['vL', '(p1.vR)'])
+        theta_i0 = npc.tensordot(theta, B_R.conj(), axes=['(p1.vR)', '(p1*.vR*)']).ireplace_label('vL*', 'vR')
+        A_L, Xi = npc.qr(theta_i0, inner_labels=['vR', 'vL'])
+    else:
+        theta_i0 = npc.tensordot(theta, Y0.conj(), axes=['(p1.vR)', '(p1*.vR*)']).ireplace_label('vL*', 'vR')
+        A_L, _ = npc.qr(theta_i0, inner_labels=['vR', 'vL'])
+        theta_i1 = npc.tensordot(A_L.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)']).ireplace_label('vR*', 'vL')
+        theta_i1.itranspose(['(p1.vR)', 'vL'])
+        B_R, Xi = npc.qr(theta_i1, inner_labels=['vL', 'vR'], inner_qconj=-1)
+        B_R.itranspose(['vL', '(p1.vR)'])
+        Xi.itranspose(['vL', 'vR'])
+    if use_eig_based_svd:
+        U, S, Vd, _, renormalization = _eig_based_svd(Xi, need_U=move_right, need_Vd=(not move_right),
+                                                      inner_labels=['vR', 'vL'], trunc_params=trunc_params)
+    else:
+        U, S, Vd, _, renormalization = svd_theta(Xi, trunc_params)
+    T_Lc, T_Rc = None, None
+    form = ['A', 'B']
+    if move_right:
+        T_Lc = npc.tensordot(A_L, U, axes=['vR', 'vL'])
+        if return_both_T:
+            if use_eig_based_svd:
+                T_Rc = npc.tensordot(Xi, B_R, axes=['vR', 'vL'])
+                T_Rc = npc.tensordot(U.conj(), T_Rc, axes=['vL*', 'vL']).ireplace_label('vR*', 'vL')
+                T_Rc = T_Rc / npc.norm(T_Rc)
+                form[1] = 'Th'
+            else:
+                T_Rc = npc.tensordot(Vd, B_R, axes=['vR', 'vL'])
+    else:
+        T_Rc = npc.tensordot(Vd, B_R, axes=['vR', 'vL'])
+        if return_both_T:
+            if use_eig_based_svd:
+                T_Lc = npc.tensordot(A_L, Xi, axes=['vR', 'vL'])
+                T_Lc = npc.tensordot(T_Lc, Vd.conj(), axes=['vR', 'vR*']).ireplace_label('vL*', 'vR')
+                T_Lc = T_Lc / npc.norm(T_Lc)
+                form[0] = 'Th'
+            else:
+                T_Lc = npc.tensordot(A_L, U, axes=['vR', 'vL'])
+    if compute_err:
+        if use_eig_based_svd:
+            theta_approx = npc.tensordot(T_Lc, T_Rc, axes=['vR', 'vL'])
+        else:
+            theta_approx = npc.tensordot(T_Lc.scale_axis(S, axis='vR'), T_Rc, axes=['vR', 'vL'])
+        N_theta = npc.norm(theta)
+        eps = npc.norm(theta / N_theta - theta_approx * (renormalization / N_theta))**2
+        trunc_err = TruncationError(eps, 1. - 2. * eps)
+    else:
+        trunc_err = TruncationError(np.nan, np.nan)
+    if T_Lc is not None:
+        T_Lc.ireplace_label('(vL.p0)', '(vL.p)')
+    if T_Rc is not None:
+        T_Rc.ireplace_label('(p1.vR)', '(p.vR)')
+    return T_Lc, S, T_Rc, form, trunc_err, renormalization

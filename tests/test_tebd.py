@@ -56,6 +56,43 @@ def _run_all(names, tol=1e-9):
             _compare('{0}_o{1}'.format(name, order), g, M, psi, eng, tol)
 
 
+def _run_qr_based(tol=1e-9):
+    """QRBasedTEBDEngine (reference tebd.py:619) against the reference: fixed numbers of imaginary-time steps through
+    update_bond_imag (sweeps) and update_bond (brick wall); the truncation errors are at rounding level here (1e-15,
+    they are sums of differences of O(1) norms), so they are compared absolutely"""
+    from tenpy_b200.models import TFIChain, SpinChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms.tebd import QRBasedTEBDEngine
+    g = h.load('tebd_qr.npz')
+    opts = {'trunc_params': {'chi_max': 24, 'svd_min': 1e-8}, 'cbe_expand': 0.1, 'cbe_expand_0': 0.5,
+            'cbe_min_block_increase': 2, 'compute_err': True}
+    L = 10
+    for name, M, state in (('tfi', TFIChain({'L': L, 'J': 1., 'g': 1.2, 'conserve': None}), ['up'] * L),
+                           ('xxz', SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 1.3, 'conserve': 'Sz'}),
+                            ['up', 'down'] * (L // 2))):
+        for tag, run in (('_imag', lambda e: (e.calc_U(2, 0.05, type_evo='imag'), e.update_imag(20))),
+                         ('_o2', lambda e: (e.calc_U(2, 0.02, type_evo='imag'), e.evolve(6, 0.02)))):
+            psi = MPS.from_product_state(M.lat_sites, state)
+            eng = QRBasedTEBDEngine(psi, M, dict(opts))
+            run(eng)
+            t = name + tag
+            Eb = M.bond_energies(psi)
+            assert np.max(np.abs(Eb - g[t + '_Ebond'])) < tol, (t, np.max(np.abs(Eb - g[t + '_Ebond'])))
+            assert np.max(np.abs(psi.entanglement_entropy() - g[t + '_S'])) < tol * 10, t
+            assert list(psi.chi) == list(g[t + '_chi']), (t, psi.chi, g[t + '_chi'])
+            assert abs(psi.norm - g[t + '_norm']) < 1e-9 * abs(g[t + '_norm']), t
+            assert abs(eng.trunc_err.eps - g[t + '_eps']) < 1e-13, t
+
+
+def test_tebd_qr_based_host_logic(fake_device):
+    _run_qr_based()
+
+
+@pytest.mark.gpu
+def test_tebd_qr_based_gpu(gpu_lib):
+    _run_qr_based()
+
+
 def test_trotter_schedules():
     from tenpy_b200.algorithms.tebd import TEBDEngine as T
     assert T.suzuki_trotter_decomposition(2, 3) == [(0, 1), (1, 0), (1, 1), (1, 0), (1, 1), (1, 0), (0, 1)]
