@@ -30,6 +30,14 @@ def use_library(lib):
     _state['lib'] = lib
     _state['scratch'] = None
     _state['out'] = None
+    # plans and index records cached on interned layouts live in the memory of the previous library's device
+    import sys
+    lay = sys.modules.get('tenpy_b200.linalg._layout')
+    if lay is not None:
+        lay._INTERN.clear()
+    npc = sys.modules.get('tenpy_b200.linalg.np_conserved')
+    if npc is not None:
+        npc._PLAN_CACHE.clear()
     return lib
 
 
