@@ -168,6 +168,9 @@ int b200_col_sqnorms_f64(int64_t rows, int64_t cols, int64_t ld, const double *X
  * replaces _svd_worker npc:4950 -> svd_robust.svd svd_robust.py:37 (LAPACK gesdd / gesvd). */
 /* switch the deflation of negligible directions in b200_block_svd_f64 on (default) / off; returns the old value */
 int b200_svd_set_deflation(int on);
+/* pivot eigen-solver of the Jacobi rounds: 1 = jacobi_eig_kernel (default), 2 = jacobi_eig_kernel_v2 (two barriers per
+ * rotation set, csrc/jacobi_eig_core.cuh; host-verified, to be timed on the GPU in round 2); returns the old value */
+int b200_svd_set_eig_variant(int variant);
 /* additional deflation threshold relative to |A_i|_F (default 0 = rounding level only): directions with a
  * singular value below tol_rel*|A_i|_F are treated like the negligible ones; returns the old value.  A DMRG
  * truncation discards them anyway (the reference's `svd_min`, truncation.py:196). */

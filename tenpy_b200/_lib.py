@@ -60,6 +60,7 @@ _SIGNATURES = {
     'b200_scale_axis_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp]),
     'b200_col_sqnorms_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     'b200_svd_set_deflation': (ctypes.c_int, [ctypes.c_int]),
+    'b200_svd_set_eig_variant': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_deflation_tol': (c_f64, [c_f64]),
     'b200_block_svd_worksize': (c_i64, [c_i64, c_i64p, c_i64p]),
     'b200_block_svd_f64': (ctypes.c_int, [c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_vp, c_vp, c_vp,
@@ -311,6 +312,10 @@ class DeviceLib:
 
     def svd_set_deflation_tol(self, tol_rel):
         return float(self.c.b200_svd_set_deflation_tol(float(tol_rel)))
+
+    def svd_set_eig_variant(self, variant):
+        """1 = jacobi_eig_kernel (default), 2 = jacobi_eig_kernel_v2; returns the old value"""
+        return int(self.c.b200_svd_set_eig_variant(int(variant)))
 
     def block_eigh(self, n, a_off, w_off, v_off, A, W, V):
         ns, ao, wo, vo = [_i64(x) for x in (n, a_off, w_off, v_off)]

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "jacobi_eig_core.cuh"
 
 namespace b200 {
 
@@ -345,6 +346,106 @@ __global__ void __launch_bounds__(JTHREADS)
     if (tid == 0) flags[blockIdx.x] = 1;
 }
 
+// Version 2 of the pivot eigen-solver (see jacobi_eig_core.cuh): the 16 disjoint rotations of a set are applied from
+// both sides in one pass over a double-buffered G -> two barriers per set instead of three, no in-place hazards.  Same
+// interface, same rotations (to rounding) as jacobi_eig_kernel; selected at run time by b200_svd_set_eig_variant(2).
+// The phase functions are the ones tests/csrc/eig_core_host.cpp checks on the CPU.
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_eig_kernel_v2(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
+                         const int *__restrict__ done, double tol_scale, const double *__restrict__ Gbuf, int nsplit,
+                         double *__restrict__ QTbuf, int *__restrict__ flags) {
+    static_assert(jeig::N == JP && jeig::LD == JLDG, "pivot order / smem stride of jacobi_eig_core.cuh");
+    __shared__ double sGa[JP * JLDG], sGb[JP * JLDG];
+    __shared__ double sQa[JP * JLDG], sQb[JP * JLDG];
+    __shared__ double s_alpha[JP], s_beta[JP];
+    __shared__ int s_partner[JP];
+    __shared__ double red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) flags[blockIdx.x] = 0;
+    const int mi = cta_mat[blockIdx.x];
+    if (done[mi]) return;
+    const JMat mt = mats[mi];
+    if (2 * (blockIdx.x - mt.cta_begin) >= mt.nb_act) return;
+    {
+        const int nch = (mt.ldy + JKC - 1) / JKC;
+        const int ns = nsplit < nch ? nsplit : nch;
+        const double *G = Gbuf + (int64_t)blockIdx.x * nsplit * (JP * JP);
+        for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+            double v = 0.0;
+            for (int sp = 0; sp < ns; ++sp) v += G[sp * (JP * JP) + idx];
+            sGa[(idx / JP) * JLDG + (idx % JP)] = v;
+        }
+    }
+    __syncthreads();
+    // ---- convergence measure of this pair (as version 1) ----
+    const double defl2 = mt.defl * mt.defl;
+    double offmax = 0.0;
+    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+        int r = idx / JP, c = idx % JP;
+        if (r < c) {
+            const double drr = sGa[r * JLDG + r], dcc = sGa[c * JLDG + c];
+            if (drr > defl2 && dcc > defl2) offmax = fmax(offmax, fabs(sGa[r * JLDG + c]) / sqrt(drr * dcc));
+        }
+    }
+    offmax = warp_max(offmax);
+    if (lane == 0) red[warp] = offmax;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int w = 0; w < JTHREADS / 32; ++w) v = fmax(v, red[w]);
+        red[0] = v;
+    }
+    __syncthreads();
+    offmax = red[0];
+    const double tol = tol_scale * sqrt((double)mt.p);
+    if (!(offmax > tol)) return;  // uniform for the whole CTA
+    if (tid == 0) atomicAdd(&rot_count[mi], 1);
+
+    // ---- G = Q L Q^T: barrier-separated phases on double buffers ----
+    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+        int r = idx / JP, c = idx % JP;
+        sQa[r * JLDG + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    double *Gc = sGa, *Gn = sGb, *Qc = sQa, *Qn = sQb;
+    const double tol_in = 1e-15;
+    for (int sweep = 0; sweep < J_INNER_SWEEPS; ++sweep) {
+        int any = 0;
+        for (int step = 0; step < JP - 1; ++step) {
+            if (tid < jeig::NPAIR) any |= jeig::phase_params(tid, step, Gc, defl2, tol_in, s_partner, s_alpha, s_beta);
+            __syncthreads();
+            for (int e = tid; e < JP * JP; e += JTHREADS)
+                jeig::phase_apply_elem(e, Gc, Gn, Qc, Qn, s_partner, s_alpha, s_beta);
+            __syncthreads();
+            double *t1 = Gc;
+            Gc = Gn;
+            Gn = t1;
+            double *t2 = Qc;
+            Qc = Qn;
+            Qn = t2;
+        }
+        if (!__syncthreads_or(any)) break;
+    }
+    // order the new rows by descending eigenvalue; rank kept in the padding column of the current G buffer
+    if (tid < JP) {
+        double di = Gc[tid * JLDG + tid];
+        int rk = 0;
+        for (int k = 0; k < JP; ++k) {
+            double dk = Gc[k * JLDG + k];
+            if (dk > di || (dk == di && k < tid)) ++rk;
+        }
+        Gc[tid * JLDG + JP] = (double)rk;
+    }
+    __syncthreads();
+    double *QT = QTbuf + (int64_t)blockIdx.x * (JP * JP);
+    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+        int i = idx / JP, k = idx % JP;
+        int rk = (int)Gc[i * JLDG + JP];
+        QT[rk * JP + k] = Qc[k * JLDG + i];
+    }
+    if (tid == 0) flags[blockIdx.x] = 1;
+}
+
 __global__ void __launch_bounds__(JTHREADS)
     jacobi_apply_kernel(double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
                         const int *__restrict__ rmap, int round, const double *__restrict__ QTbuf,
@@ -508,6 +609,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- host driver -----------------------------------------------------------------------------------
+static int g_eig_variant = 1;   // pivot eigen-solver: 1 = jacobi_eig_kernel (GPU-verified), 2 = jacobi_eig_kernel_v2
 struct JLayout {
     std::vector<JMat> mats;
     std::vector<int> cta_mat;
@@ -646,8 +748,12 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
             jacobi_gram_kernel<<<dim3((unsigned)nsplit, (unsigned)n_cta), JTHREADS, jacobi_smem_bytes(), st>>>(
                 wf, d_mats, d_cta, d_rmap, round_counter, d_done, d_G);
             B200_CHECK_LAUNCH();
-            jacobi_eig_kernel<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit, d_QT,
-                                                        d_flags);
+            if (g_eig_variant == 2)
+                jacobi_eig_kernel_v2<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit,
+                                                               d_QT, d_flags);
+            else
+                jacobi_eig_kernel<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit, d_QT,
+                                                            d_flags);
             B200_CHECK_LAUNCH();
             jacobi_apply_kernel<<<dim3((unsigned)nsplit, (unsigned)n_cta, 2), JTHREADS, jacobi_smem_bytes(), st>>>(
                 wf, d_mats, d_cta, d_rmap, round_counter, d_QT, d_flags);
@@ -756,6 +862,12 @@ extern "C" double b200_svd_set_deflation_tol(double tol_rel) {
     g_svd_defl_rel = tol_rel > 0.0 ? tol_rel : 0.0;
     return old;
 }
+extern "C" int b200_svd_set_eig_variant(int variant) {
+    int old = g_eig_variant;
+    if (variant == 1 || variant == 2) g_eig_variant = variant;
+    return old;
+}
+
 extern "C" int b200_svd_set_deflation(int on) {
     int old = g_svd_deflation;
     g_svd_deflation = on ? 1 : 0;

@@ -1,0 +1,57 @@
+"""dev check (NOT collected by pytest; run by hand on the GPU box first thing in round 2):
+
+    python tests/dev_eig_v2_gpu_check.py
+
+Switches the pivot eigen-solver of the Jacobi rounds to `jacobi_eig_kernel_v2` (b200_svd_set_eig_variant(2)), compares
+SVD / eigh results with version 1 and with numpy on a set of shapes, and times a generic 2048x2048 block with both."""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, '.')
+from tenpy_b200 import backend
+from tenpy_b200.linalg import np_conserved as npc
+
+
+def main():
+    lib = backend.get_lib()
+    rng = np.random.default_rng(3)
+    ok = True
+    for shape in [(5, 5), (33, 47), (64, 64), (200, 150), (512, 512)]:
+        A = rng.standard_normal(shape) * np.logspace(0, -6, shape[1])[None, :]
+        a = npc.Array.from_ndarray_trivial(A)
+        res = {}
+        for variant in (1, 2):
+            old = lib.svd_set_eig_variant(variant)
+            try:
+                U, S, VH = npc.svd(a)
+            finally:
+                lib.svd_set_eig_variant(old)
+            rec = np.max(np.abs(U.to_ndarray() @ np.diag(S) @ VH.to_ndarray() - A))
+            sd = np.max(np.abs(np.sort(S)[::-1] - np.linalg.svd(A, compute_uv=False)))
+            orth = np.max(np.abs(U.to_ndarray().T @ U.to_ndarray() - np.eye(min(shape))))
+            res[variant] = (rec, sd, orth, npc.svd_stats['jacobi_sweeps'][-1])
+        print(shape, 'v1 rec %.1e dS %.1e orth %.1e sweeps %d | v2 rec %.1e dS %.1e orth %.1e sweeps %d' % (res[1] + res[2]))
+        ok = ok and res[2][0] < 1e-11 and res[2][1] < 1e-11 and res[2][2] < 1e-11
+    n = 2048
+    th = npc.Array.from_ndarray_trivial(rng.standard_normal((n, n)))
+    for variant in (1, 2):
+        old = lib.svd_set_eig_variant(variant)
+        try:
+            npc.svd(th)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            npc.svd(th)
+            torch.cuda.synchronize()
+            print('2048x2048 generic, eig variant %d: %.1f ms, %d sweeps' % (variant, (time.perf_counter() - t0) * 1e3,
+                                                                            npc.svd_stats['jacobi_sweeps'][-1]))
+        finally:
+            lib.svd_set_eig_variant(old)
+    print('ok' if ok else 'FAILED')
+    return 0 if ok else 1
+
+
+if __name__ == '__main__':
+    sys.exit(main())

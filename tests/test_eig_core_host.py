@@ -1,0 +1,20 @@
+"""CPU check of the version-2 pivot eigen-solver of the Jacobi SVD (tenpy_b200/csrc/jacobi_eig_core.cuh): the phase
+functions the CUDA kernel `jacobi_eig_kernel_v2` calls between barriers are compiled for the host and run thread by
+thread (tests/csrc/eig_core_host.cpp), next to a sequential restatement of the GPU-verified version 1."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+def test_eig_core_phases_on_host(tmp_path):
+    exe = str(tmp_path / 'eig_core_host')
+    src = os.path.join(ROOT, 'tests', 'csrc', 'eig_core_host.cpp')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-Wall', '-o', exe, src])
+    out = subprocess.run([exe, '60'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr
+    assert out.stdout.strip().endswith('ok')
