@@ -148,6 +148,13 @@ int b200_take_blocks_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t
 int b200_scale_axis_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t *task_host,
                         const double *S_dev, double *X, b200_stream_t stream);
 
+/* OUT[o, n, i] = sum_k M[n, k] T[o, k, i]  (T: outer x K x inner, OUT: outer x N x inner, row-major, i contiguous;
+ * M: N x K on the device, K <= 32): a small matrix applied to the middle index without changing the layout.  Fuses the
+ * two block transpositions and the skinny GEMM npc.tensordot needs for "W0.W1 applied to LP.theta" in the split-order
+ * matvec (TwoSiteH.matvec, reference mps_common.py:1341-1343) into one streaming pass.  Opt-in (round 2: GPU timing). */
+int b200_mid_contract_f64(int64_t K, int64_t N, int64_t outer, int64_t inner, const double *M_dev, const double *T,
+                          double *OUT, b200_stream_t stream);
+
 /* OUT[c] = sum_r X[r*ld + c]^2 for a row-major (rows x cols) matrix (leverage scores of the null-space
  * completion in np_conserved.svd; no reference counterpart: LAPACK returns a complete basis by itself) */
 int b200_col_sqnorms_f64(int64_t rows, int64_t cols, int64_t ld, const double *X, double *OUT,

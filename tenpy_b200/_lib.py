@@ -59,6 +59,7 @@ _SIGNATURES = {
     'b200_take_blocks_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp, c_vp]),
     'b200_scale_axis_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp]),
     'b200_col_sqnorms_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'b200_mid_contract_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'b200_svd_set_deflation': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_eig_variant': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_deflation_tol': (c_f64, [c_f64]),
@@ -286,6 +287,12 @@ class DeviceLib:
         with _Prof(self, 'move'):
             self._check(self.c.b200_scale_axis_f64(th.shape[0], _ptr(task_dev), thp, _ptr(S_dev), _ptr(X),
                                                    self.stream()))
+
+    def mid_contract(self, K, N, outer, inner, M, T, OUT):
+        """OUT[o, n, i] = sum_k M[n, k] T[o, k, i] (include/b200npc.h)"""
+        with _Prof(self, 'move'):
+            self._check(self.c.b200_mid_contract_f64(int(K), int(N), int(outer), int(inner), _ptr(M), _ptr(T),
+                                                     _ptr(OUT), self.stream()))
 
     # -- decompositions
     def block_svd(self, m, n, a_off, u_off, s_off, vt_off, A, U, S, VT):

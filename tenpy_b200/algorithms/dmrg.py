@@ -364,6 +364,8 @@ class TwoSiteDMRGEngine:
         """Reference mps_common.py:498."""
         self.eff_H = self.EffectiveH(self.env, self.i0, self.combine, self.move_right,
                                       matvec_order=self.options.get('matvec_order', 'auto'))
+        if 'mpo_apply' in self.options:
+            self.eff_H.mpo_apply = self.options['mpo_apply']
         theta = self.psi.get_theta(self.i0, n=self.n_optimize)
         return self.eff_H.combine_theta(theta)
 

@@ -147,6 +147,9 @@ class TwoSiteH:
     length = 2
     acts_on = ['vL', 'p0', 'p1', 'vR']
     SPLIT_MIN_BLOCK = 1 << 20
+    # 'tensordot': W0.W1 is applied to LP.theta by npc.tensordot (two block transpositions + a skinny GEMM);
+    # 'fused': by the streaming kernel b200_mid_contract_f64 (no charges / one block only).  Opt-in until timed on the GPU.
+    mpo_apply = 'tensordot'
 
     def __init__(self, env, i0, combine=False, move_right=True, matvec_order='auto'):
         if matvec_order not in ('auto', 'combined', 'split'):
@@ -195,11 +198,41 @@ class TwoSiteH:
             self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])   # wL p0 p0* p1 p1* wR  (D^2 d^4 numbers)
         th = theta.split_legs(['(vL.p0)', '(p1.vR)'])                        # vL p0 p1 vR
         th = npc.tensordot(self.LP, th, axes=['vR', 'vL'])                   # vR* wR p0 p1 vR      2 D d^2 chi^3
-        th = npc.tensordot(th, self._W01, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])  # vR* vR p0 p1 wR
-        th = npc.tensordot(th, self.RP, axes=[['vR', 'wR'], ['vL', 'wL']])   # vR* p0 p1 vL*       2 D d^2 chi^3
+        fused = self._apply_W01_fused(th) if self.mpo_apply == 'fused' else None
+        if fused is not None:
+            th = npc.tensordot(fused, self._RP_t, axes=[['wR', 'vR'], ['wL', 'vL']])   # no transposition left
+        else:
+            th = npc.tensordot(th, self._W01, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])  # vR* vR p0 p1 wR
+            th = npc.tensordot(th, self.RP, axes=[['vR', 'wR'], ['vL', 'wL']])   # vR* p0 p1 vL*   2 D d^2 chi^3
         th.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
         th = th.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR])
         return th.itranspose(labels)
+
+    def _apply_W01_fused(self, th):
+        """``W0.W1`` applied to ``th[vR*, wR, p0, p1, vR]`` in one streaming pass that keeps the layout: the result
+        ``[vR*, p0, p1, wR, vR]`` is directly the left operand of the contraction with `RP`.  Dense (one block) only;
+        returns None if not applicable."""
+        from .. import backend
+        W01 = self._W01
+        if th._layout.nblocks != 1 or W01._layout.nblocks != 1 or th.get_leg_labels() != ['vR*', 'wR', 'p0', 'p1', 'vR']:
+            return None
+        if getattr(self, '_W01_mat', None) is None:
+            M = W01.transpose(['p0', 'p1', 'wR', 'wL', 'p0*', 'p1*'])        # [(p0' p1' wR'), (wL p0 p1)], one block
+            self._W01_mat = M
+            self._RP_t = self.RP.transpose(['wL', 'vL', 'vL*'])
+        M = self._W01_mat
+        chi_l, D, d0, d1, chi_r = th.shape
+        K = D * d0 * d1
+        N = M.shape[0] * M.shape[1] * M.shape[2]
+        if K > 32 or M.size != N * K:
+            return None
+        legs = [th.legs[0], M.legs[0], M.legs[1], M.legs[2], th.legs[4]]
+        res = npc.Array(legs, np.float64, th.chinfo.make_valid(th.qtotal + W01.qtotal),
+                        ['vR*', 'p0', 'p1', 'wR', 'vR'])
+        lay, _ = npc.BlockLayout.from_legs(legs, np.zeros((1, 5), np.int64))
+        buf = backend.zeros(lay.size) if lay.has_padding else backend.empty(lay.size)
+        backend.get_lib().mid_contract(K, N, chi_l, chi_r, M._buf, th._buf, buf)
+        return res._set_blocks(lay, buf)
 
     def combine_Heff(self, env, left=True, right=True):
         """Reference mps_common.py:1350."""

@@ -7,6 +7,7 @@
 // The integer "index plans" (records below) are computed on the host once per block layout and cached in
 // device memory by the caller; a whole Array is moved by ONE launch.
 #include "common.cuh"
+#include "mid_contract_core.cuh"
 
 namespace b200 {
 
@@ -101,9 +102,40 @@ __global__ void __launch_bounds__(MV_THREADS) col_sqnorms_kernel(int64_t rows, i
     out[c] = s;
 }
 
+// OUT[o, n, i] = sum_k M[n, k] T[o, k, i]  (mid_contract_core.cuh); grid.x over i (256 per CTA), grid.y over o
+template <int KMAX>
+__global__ void __launch_bounds__(MV_THREADS) mid_contract_kernel(int K, int N, int64_t outer, int64_t inner,
+                                                                  const double *__restrict__ M,
+                                                                  const double *__restrict__ T,
+                                                                  double *__restrict__ OUT) {
+    extern __shared__ double sM[];
+    for (int idx = threadIdx.x; idx < N * K; idx += blockDim.x) sM[idx] = M[idx];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= inner) return;
+    for (int64_t o = blockIdx.y; o < outer; o += gridDim.y) midc::column<KMAX>(o, i, K, N, inner, sM, T, OUT);
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_mid_contract_f64(int64_t K, int64_t N, int64_t outer, int64_t inner, const double *M_dev,
+                                     const double *T, double *OUT, b200_stream_t stream) {
+    if (outer <= 0 || inner <= 0 || N <= 0) return B200_OK;
+    if (K <= 0 || K > 32 || N > 1024) return set_error(B200_ERR_ARG, "mid_contract: K=%lld (1..32), N=%lld (<=1024)",
+                                                        (long long)K, (long long)N);
+    const unsigned gx = (unsigned)((inner + MV_THREADS - 1) / MV_THREADS);
+    const unsigned gy = (unsigned)(outer < 65535 ? outer : 65535);
+    const size_t smem = (size_t)(N * K) * sizeof(double);
+    if (smem > 48 * 1024) return set_error(B200_ERR_ARG, "mid_contract: matrix %lld x %lld too large", (long long)N, (long long)K);
+    if (K <= 16)
+        mid_contract_kernel<16><<<dim3(gx, gy), MV_THREADS, smem, (cudaStream_t)stream>>>((int)K, (int)N, outer, inner, M_dev, T, OUT);
+    else
+        mid_contract_kernel<32><<<dim3(gx, gy), MV_THREADS, smem, (cudaStream_t)stream>>>((int)K, (int)N, outer, inner, M_dev, T, OUT);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
 
 extern "C" int b200_col_sqnorms_f64(int64_t rows, int64_t cols, int64_t ld, const double *X, double *OUT,
                                     b200_stream_t stream) {

@@ -1,5 +1,6 @@
 """dev probe (not a test): effective-H matvec at a saturated centre bond, reference order (LHeff.theta.RHeff,
-4 D d^3 chi^3 flop) against the 'split' order (LP, W0 W1, RP on the split theta, 4 D d^2 chi^3 flop).
+4 D d^3 chi^3 flop) against the 'split' order (LP, W0 W1, RP on the split theta, 4 D d^2 chi^3 flop) and the split order
+with the fused W0.W1 application (b200_mid_contract_f64, opt-in).
 
     python tests/dev_matvec_order_probe.py [chi=1024] [L=24] [reps=10]
 
@@ -35,8 +36,10 @@ def main():
     eng.env.get_RP(i0 + 1, store=True)
     cuda = lib.device.type == 'cuda'
     out = {}
-    for order in ('combined', 'split'):
-        H = TwoSiteH(eng.env, i0, combine=True, matvec_order=order)
+    for order in ('combined', 'split', 'split+fused'):
+        H = TwoSiteH(eng.env, i0, combine=True, matvec_order=order.split('+')[0])
+        if order.endswith('fused'):      # b200_mid_contract_f64 (opt-in kernel, round 2: first GPU run)
+            H.mpo_apply = 'fused'
         theta = H.combine_theta(psi.get_theta(i0, 2))
         for _ in range(3):
             res = H.matvec(theta)
@@ -63,8 +66,9 @@ def main():
                           'wall_ms': round(wall, 4), 'family_ms': fam,
                           'reference_equivalent_tflops': 4. * D * d**3 * chi**3 / (ms * 1e-3) / 1e12}))
     diff = npc.norm(out['combined'] - out['split']) / npc.norm(out['combined'])
-    print(json.dumps({'rel_diff_split_vs_combined': diff}))
-    assert diff < 1e-12
+    diff_f = npc.norm(out['combined'] - out['split+fused']) / npc.norm(out['combined'])
+    print(json.dumps({'rel_diff_split_vs_combined': diff, 'rel_diff_fused_vs_combined': diff_f}))
+    assert diff < 1e-12 and diff_f < 1e-12
 
 
 if __name__ == '__main__':

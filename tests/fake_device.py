@@ -125,6 +125,12 @@ class FakeDeviceLib:
             v = x[off:off + outer * ln * inner].reshape(outer, ln, inner)
             v *= s[soff:soff + ln][None, :, None]
 
+    def mid_contract(self, K, N, outer, inner, M, T, OUT):
+        self._count('mid_contract')
+        m = M.numpy()[:N * K].reshape(N, K)
+        t = T.numpy()[:outer * K * inner].reshape(outer, K, inner)
+        OUT.numpy()[:outer * N * inner] = np.einsum('nk,oki->oni', m, t).reshape(-1)
+
     deflation = True
     deflation_tol = 0.
 

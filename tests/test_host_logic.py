@@ -294,3 +294,39 @@ def test_dmrg_driver_split_matvec(fake_device):
     res, psi = _run_dmrg(M, ['up', 'down'] * (L // 2), opts)
     assert abs(res['E'] - g['xxz_E']) < 1e-10 * abs(g['xxz_E'])
     assert np.max(np.abs(psi.entanglement_entropy() - g['xxz_S'])) < 1e-7
+
+
+def test_matvec_fused_mpo_apply(fake_device):
+    """split-order matvec with `mpo_apply='fused'` (b200_mid_contract_f64: W0.W1 applied to the middle legs in one
+    streaming pass) equals the tensordot route; only taken for dense (one block) tensors"""
+    from tenpy_b200.models import TFIChain, SpinChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg import np_conserved as npc
+    M = TFIChain({'L': 8, 'J': 1., 'g': 1.1, 'conserve': None})
+    psi = MPS.from_product_state(M.lat_sites, ['up'] * 8)
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': None, 'combine': True, 'trunc_params': {'chi_max': 24, 'svd_min': 1e-12}})
+    eng.sweep()
+    eng.sweep()
+    for i0 in range(7):
+        Ht = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+        Hf = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+        Hf.mpo_apply = 'fused'
+        theta = Ht.combine_theta(psi.get_theta(i0, 2))
+        n0 = fake_device.calls.get('mid_contract', 0)
+        a, b = Ht.matvec(theta), Hf.matvec(theta)
+        assert fake_device.calls.get('mid_contract', 0) == n0 + 1
+        assert a.get_leg_labels() == b.get_leg_labels()
+        assert npc.norm(a - b) <= 1e-13 * max(npc.norm(a), 1e-300)
+    # whole run with the option; with charges the fused route silently falls back to tensordot
+    g = h.load('dmrg.npz')
+    M = TFIChain({'L': 20, 'J': 1., 'g': 1., 'conserve': None})
+    res, psi = _run_dmrg(M, ['up'] * 20, {'mixer': None, 'max_E_err': 1e-10, 'combine': True, 'matvec_order': 'split',
+                                         'mpo_apply': 'fused', 'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
+    assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
+    M = SpinChain({'L': 8, 'Jx': 1., 'Jy': 1., 'Jz': 1., 'conserve': 'Sz'})
+    n0 = fake_device.calls.get('mid_contract', 0)
+    _run_dmrg(M, ['up', 'down'] * 4, {'mixer': True, 'matvec_order': 'split', 'mpo_apply': 'fused', 'max_sweeps': 3,
+                                     'trunc_params': {'chi_max': 16, 'svd_min': 1e-10}})
+    assert fake_device.calls.get('mid_contract', 0) == n0
