@@ -125,6 +125,15 @@ int b200_dot_segments_f64(int64_t n_seg, const int64_t *seg_dev, int64_t max_len
  * replaces the two iadd_prefactor_other + norm calls of krylov_based.py:665-671 */
 int b200_lanczos_update_f64(int64_t n, double alpha, const double *V1, double beta, const double *V0,
                             double *W, double *scratch_dev, double *out_dev, b200_stream_t stream);
+/* the same step with device-resident scalars: alpha = alpha_dev[0] (written there by b200_dot_f64),
+ * beta = sqrt(beta2_dev[0]) (the |w|^2 of the previous step; beta2_dev / V0 may be NULL), and x *= 1/sqrt(norm2_dev[0]).
+ * A Lanczos iteration (krylov_based.py:645-676) then needs no host round trip; the (alpha, beta) pairs are read back
+ * in chunks for the tridiagonal eigenproblem and the convergence test.  Bit-identical to the host-scalar route.
+ * Opt-in (lanczos_params['device_scalars']) until timed on the GPU. */
+int b200_lanczos_update_dev_f64(int64_t n, const double *alpha_dev, const double *V1, const double *beta2_dev,
+                                const double *V0, double *W, double *scratch_dev, double *out_dev,
+                                b200_stream_t stream);
+int b200_scal_rsqrt_dev_f64(int64_t n, const double *norm2_dev, double *X, b200_stream_t stream);
 
 /* ---- block data movement ------------------------------------------------------------------------- */
 /* Strided N-d block copies: dst[doff + sum_i idx_i*dstride_i] = src[soff + sum_i idx_i*sstride_i].

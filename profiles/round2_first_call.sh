@@ -1,0 +1,10 @@
+#!/bin/bash
+# First GPU call of round 2: the opt-in kernels written in round 1 after the GPU budget was spent (all host-checked, none
+# GPU-run yet).  Each step has its own timeout; outputs under gpurun_out/r02a_*.
+set -x
+T=gpurun_out
+mkdir -p $T
+timeout 300 python -m pytest tests -m gpu -x -q > $T/r02a_gpu_tests.log 2>&1; tail -n 3 $T/r02a_gpu_tests.log
+timeout 180 python tests/dev_eig_v2_gpu_check.py > $T/r02a_eig_v2.log 2>&1; tail -n 12 $T/r02a_eig_v2.log
+timeout 180 python tests/dev_matvec_order_probe.py 1024 24 10 > $T/r02a_matvec_probe.log 2>&1; tail -n 5 $T/r02a_matvec_probe.log
+timeout 300 python tests/dev_optins_gpu_check.py 1024 24 > $T/r02a_optins.log 2>&1; tail -n 6 $T/r02a_optins.log

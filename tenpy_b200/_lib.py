@@ -55,6 +55,8 @@ _SIGNATURES = {
     'b200_axpy_segments_f64': (ctypes.c_int, [c_i64, c_vp, c_i64, c_f64, c_vp, c_vp, c_vp]),
     'b200_dot_segments_f64': (ctypes.c_int, [c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200_lanczos_update_f64': (ctypes.c_int, [c_i64, c_f64, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'b200_lanczos_update_dev_f64': (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'b200_scal_rsqrt_dev_f64': (ctypes.c_int, [c_i64, c_vp, c_vp, c_vp]),
     'b200_copy_blocks_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp]),
     'b200_take_blocks_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp, c_vp]),
     'b200_scale_axis_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp]),
@@ -268,6 +270,17 @@ class DeviceLib:
         with _Prof(self, 'blas1'):
             self._check(self.c.b200_lanczos_update_f64(n, float(alpha), _ptr(V1), float(beta), _ptr(V0), _ptr(W),
                                                        _ptr(scratch), _ptr(out), self.stream()))
+
+    def lanczos_update_dev(self, n, alpha_dev, V1, beta2_dev, V0, W, scratch, out):
+        """w -= alpha_dev[0] v1 + sqrt(beta2_dev[0]) v0, out[0] = |w|^2: scalars stay on the device"""
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_lanczos_update_dev_f64(n, _ptr(alpha_dev), _ptr(V1), _ptr(beta2_dev), _ptr(V0),
+                                                           _ptr(W), _ptr(scratch), _ptr(out), self.stream()))
+
+    def scal_rsqrt_dev(self, n, norm2_dev, X):
+        """x *= 1 / sqrt(norm2_dev[0])"""
+        with _Prof(self, 'blas1'):
+            self._check(self.c.b200_scal_rsqrt_dev_f64(n, _ptr(norm2_dev), _ptr(X), self.stream()))
 
     # -- data movement
     def copy_blocks(self, task_host, task_dev, SRC, DST):

@@ -116,6 +116,40 @@ __global__ void __launch_bounds__(B1_THREADS) lanczos_update_kernel(int64_t n, d
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
+// the same step with the scalars left on the device: alpha = *alpha_p, beta = sqrt(*beta2_p) (beta2_p / v0 may be null).
+// sqrt and the division below are IEEE correctly rounded for double: bit-identical to the host-scalar route.
+__global__ void __launch_bounds__(B1_THREADS) lanczos_update_dev_kernel(int64_t n, const double *__restrict__ alpha_p,
+                                                                        const double *__restrict__ v1,
+                                                                        const double *__restrict__ beta2_p,
+                                                                        const double *__restrict__ v0,
+                                                                        double *__restrict__ w,
+                                                                        double *__restrict__ partial) {
+    __shared__ double red[32];
+    const double alpha = alpha_p[0];
+    const bool have0 = (v0 != nullptr) && (beta2_p != nullptr);
+    const double beta = have0 ? sqrt(beta2_p[0]) : 0.0;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double s = 0.0;
+    for (int64_t j = i; j < n; j += stride) {
+        double r = w[j];
+        r = fma(-alpha, v1[j], r);
+        if (have0) r = fma(-beta, v0[j], r);
+        w[j] = r;
+        s = fma(r, r, s);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// x *= 1 / sqrt(*norm2_p)
+__global__ void __launch_bounds__(B1_THREADS) scal_rsqrt_dev_kernel(int64_t n, const double *__restrict__ norm2_p,
+                                                                    double *__restrict__ x) {
+    const double a = 1.0 / sqrt(norm2_p[0]);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        x[j] *= a;
+}
+
 // segment kernels: blockIdx.y = segment, blockIdx.x strides over the segment
 __global__ void __launch_bounds__(B1_THREADS) axpy_seg_kernel(const int64_t *__restrict__ seg, double alpha,
                                                               const double *__restrict__ x, double *__restrict__ y) {
@@ -181,6 +215,29 @@ extern "C" int b200_lanczos_update_f64(int64_t n, double alpha, const double *V1
     lanczos_update_kernel<<<grid, B1_THREADS, 0, (cudaStream_t)stream>>>(n, alpha, V1, beta, V0, W, scratch);
     B200_CHECK_LAUNCH();
     dot_final_kernel<<<1, B1_THREADS, 0, (cudaStream_t)stream>>>(grid, scratch, out);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_lanczos_update_dev_f64(int64_t n, const double *alpha_dev, const double *V1, const double *beta2_dev,
+                                           const double *V0, double *W, double *scratch, double *out,
+                                           b200_stream_t stream) {
+    int grid = b1_grid(n, 8);
+    if (grid > B200_DOT_SCRATCH) grid = B200_DOT_SCRATCH;
+    if (n <= 0) {
+        B200_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double), (cudaStream_t)stream));
+        return B200_OK;
+    }
+    lanczos_update_dev_kernel<<<grid, B1_THREADS, 0, (cudaStream_t)stream>>>(n, alpha_dev, V1, beta2_dev, V0, W, scratch);
+    B200_CHECK_LAUNCH();
+    dot_final_kernel<<<1, B1_THREADS, 0, (cudaStream_t)stream>>>(grid, scratch, out);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_scal_rsqrt_dev_f64(int64_t n, const double *norm2_dev, double *X, b200_stream_t stream) {
+    if (n <= 0) return B200_OK;
+    scal_rsqrt_dev_kernel<<<b1_grid(n, 8), B1_THREADS, 0, (cudaStream_t)stream>>>(n, norm2_dev, X);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

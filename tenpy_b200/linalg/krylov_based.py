@@ -80,6 +80,9 @@ class LanczosGroundState(KrylovBased):
         self.N_cache = int(self.options.get('N_cache', self.N_max))
         if self.N_cache < 2:
             raise ValueError('Need to cache at least two vectors.')
+        # extension (opt-in): keep (alpha, beta) on the device and read them back in chunks, see _build_krylov_device
+        self.device_scalars = bool(self.options.get('device_scalars', False))
+        self.sync_every = max(1, int(self.options.get('sync_every', 2)))
 
     def run(self):
         """Returns ``(E0, psi0, N)`` (reference krylov_based.py:614)."""
@@ -89,8 +92,65 @@ class LanczosGroundState(KrylovBased):
             return E0, self.psi0.copy(), N
         return E0, self._calc_result_full(N), N
 
+    def _build_krylov_device(self):
+        """The recurrence of :meth:`_build_krylov` without a host round trip per iteration: ``alpha_k`` (written by the
+        dot kernel) and ``|w|^2`` stay in a small device array, the update and the normalisation read them there
+        (``b200_lanczos_update_dev_f64``, ``b200_scal_rsqrt_dev_f64``; bit-identical arithmetic).  The scalars come
+        back in chunks -- after the first `N_min` iterations (nothing can converge earlier), then every `sync_every`
+        -- and the reference's bookkeeping (tridiagonal `eigh`, `_converged`, breakdown test) is replayed on the host
+        for every ``k`` of the chunk in order: the run stops at exactly the ``k`` the reference stops at, iterations
+        enqueued beyond it are discarded (their vectors are dropped from the cache).  Returns ``N`` or ``None`` if the
+        vectors do not share one block layout (caller falls back to the host-scalar loop)."""
+        h = self._h_krylov
+        lib = backend.get_lib()
+        w = self.psi0
+        beta0 = npc.norm(w)
+        if beta0 < self._cutoff:
+            raise ValueError('Norm of self.psi0 too small: {0!s}'.format(beta0))
+        if self._psi0_norm is None:
+            self._psi0_norm = beta0
+        sc = backend.zeros(2 * self.N_max)             # sc[2k] = alpha_k, sc[2k+1] = |w_k|^2 = beta_{k+1}^2
+        scratch = backend.dot_scratch()
+        done_k = 0                                     # iterations whose scalars have been processed on the host
+        k = 0
+        while k < self.N_max:
+            stop_at = self.N_min if k < self.N_min else min(self.N_max, k + self.sync_every)
+            while k < stop_at:
+                if k == 0:
+                    w.iscale_prefactor(1. / beta0)
+                else:
+                    lib.scal_rsqrt_dev(w._layout.size, sc[2 * k - 1:2 * k], w._buf)
+                self._to_cache(w)
+                w = self.H.matvec(w)
+                v1 = self._cache[-1]
+                if not (w._layout is v1._layout or w._layout.same_blocks(v1._layout)):
+                    return None
+                lib.dot(w._layout.size, w._buf, v1._buf, scratch, sc[2 * k:2 * k + 1])
+                v0 = self._cache[-2]._buf if k > 0 else None
+                lib.lanczos_update_dev(w._layout.size, sc[2 * k:2 * k + 1], v1._buf,
+                                       sc[2 * k - 1:2 * k] if k > 0 else None, v0, w._buf, scratch,
+                                       sc[2 * k + 1:2 * k + 2])
+                k += 1
+            vals = backend.to_host(sc[:2 * k])                        # the one synchronisation of this chunk
+            for kk in range(done_k, k):
+                h[kk, kk] = vals[2 * kk]
+                self._calc_result_krylov(kk)
+                beta = float(np.sqrt(vals[2 * kk + 1]))
+                h[kk, kk + 1] = h[kk + 1, kk] = beta
+                if not np.isfinite(beta) or abs(beta) < self._cutoff or (kk + 1 >= self.N_min and self._converged(kk)):
+                    for _ in range(k - (kk + 1)):                     # vectors of the discarded iterations
+                        self._cache.pop()
+                    return kk + 1
+            done_k = k
+        return k
+
     def _build_krylov(self):
         """Reference krylov_based.py:645."""
+        if self.device_scalars and not self.reortho and self.N_cache >= self.N_max:
+            N = self._build_krylov_device()
+            if N is not None:
+                return N
+            self._cache = []
         h = self._h_krylov
         w = self.psi0
         beta = npc.norm(w)

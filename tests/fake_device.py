@@ -97,6 +97,19 @@ class FakeDeviceLib:
             w[:n] -= beta * V0.numpy()[:n]
         out.numpy()[0] = float(np.dot(w[:n], w[:n]))
 
+    def lanczos_update_dev(self, n, alpha_dev, V1, beta2_dev, V0, W, scratch, out):
+        self._count('lanczos_update_dev')
+        w = W.numpy()
+        w[:n] -= float(alpha_dev.numpy()[0]) * V1.numpy()[:n]
+        if V0 is not None and beta2_dev is not None:
+            w[:n] -= float(np.sqrt(beta2_dev.numpy()[0])) * V0.numpy()[:n]
+        out.numpy()[0] = float(np.dot(w[:n], w[:n]))
+
+    def scal_rsqrt_dev(self, n, norm2_dev, X):
+        self._count('scal_rsqrt_dev')
+        with np.errstate(divide='ignore', invalid='ignore'):
+            X.numpy()[:n] *= 1. / np.sqrt(norm2_dev.numpy()[0])
+
     def copy_blocks(self, task_host, task_dev, SRC, DST):
         self._count('copy_blocks')
         src, dst = SRC.numpy(), DST.numpy()

@@ -330,3 +330,47 @@ def test_matvec_fused_mpo_apply(fake_device):
     _run_dmrg(M, ['up', 'down'] * 4, {'mixer': True, 'matvec_order': 'split', 'mpo_apply': 'fused', 'max_sweeps': 3,
                                      'trunc_params': {'chi_max': 16, 'svd_min': 1e-10}})
     assert fake_device.calls.get('mid_contract', 0) == n0
+
+
+def test_lanczos_device_scalars(fake_device):
+    """Lanczos with device-resident (alpha, beta) read back in chunks stops at the same Krylov dimension and returns the
+    same vector as the host-scalar loop: fixed N (the benchmark setting), early convergence inside a chunk, breakdown
+    (start vector = eigenvector), and whole DMRG runs"""
+    from tenpy_b200.models import TFIChain, SpinChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg.krylov_based import LanczosGroundState
+    from tenpy_b200.linalg import np_conserved as npc
+    M = SpinChain({'L': 10, 'Jx': 1., 'Jy': 1., 'Jz': 0.7, 'conserve': 'Sz'})
+    psi = MPS.from_product_state(M.lat_sites, ['up', 'down'] * 5)
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': True, 'trunc_params': {'chi_max': 20, 'svd_min': 1e-12}})
+    eng.sweep()
+    eng.sweep()
+    H = TwoSiteH(eng.env, 4, combine=True)
+    rng = np.random.default_rng(2)
+    theta0 = H.combine_theta(psi.get_theta(4, 2))
+    noise = npc.Array.from_func(rng.standard_normal, theta0.legs, qtotal=theta0.qtotal, labels=theta0.get_leg_labels())
+    start = theta0 + noise * 0.3
+    for opts in ({'N_min': 10, 'N_max': 10}, {'N_min': 2, 'N_max': 20, 'P_tol': 1e-8}, {'N_min': 3, 'N_max': 20},
+                 {'N_min': 2, 'N_max': 20, 'sync_every': 5, 'P_tol': 1e-6}):
+        E0, v0, N0 = LanczosGroundState(H, start.copy(deep=True), dict(opts)).run()
+        n_before = fake_device.calls.get('lanczos_update_dev', 0)
+        E1, v1, N1 = LanczosGroundState(H, start.copy(deep=True), dict(opts, device_scalars=True)).run()
+        assert fake_device.calls.get('lanczos_update_dev', 0) >= n_before + N0
+        assert N1 == N0 and abs(E1 - E0) < 1e-13 * max(1., abs(E0))
+        assert npc.norm(v1 - v0) < 1e-12
+    # breakdown: the exact ground state of the block as start vector
+    Eg, vg, _ = LanczosGroundState(H, start.copy(deep=True), {'N_min': 2, 'N_max': 40, 'P_tol': 1e-28}).run()
+    for dev in (False, True):
+        E2, v2, N2 = LanczosGroundState(H, vg.copy(deep=True), {'N_min': 2, 'N_max': 12, 'device_scalars': dev}).run()
+        assert abs(E2 - Eg) < 1e-12 and abs(abs(npc.inner(v2, vg, axes='range', do_conj=True)) - 1.) < 1e-12
+        assert np.all(np.isfinite(v2.to_ndarray()))
+    # whole runs
+    g = h.load('dmrg.npz')
+    M = TFIChain({'L': 20, 'J': 1., 'g': 1., 'conserve': None})
+    res, psi = _run_dmrg(M, ['up'] * 20, {'mixer': None, 'max_E_err': 1e-10, 'combine': True,
+                                         'lanczos_params': {'device_scalars': True},
+                                         'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
+    assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
+    assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
