@@ -15,6 +15,36 @@ from ..linalg.truncation import truncate
 __all__ = ['OneSiteH', 'TwoSiteH', 'Mixer', 'DensityMatrixMixer', 'SubspaceExpansion']
 
 
+def _apply_chain(obj, theta, chain, relabel):
+    """Run a contraction recipe: `chain` = sequence of ``(side, attribute, axes_of_tensor, axes_of_theta)``; ``side``
+    'L' contracts ``tensor . theta``, 'R' contracts ``theta . tensor``; `relabel` = (old, new) bra -> ket labels.
+    Every step is one grouped GEMM launch (plus block transpositions where the leg order requires them)."""
+    for side, attr, ax_t, ax_th in chain:
+        tensor = getattr(obj, attr)
+        theta = npc.tensordot(tensor, theta, axes=[ax_t, ax_th]) if side == 'L' else \
+            npc.tensordot(theta, tensor, axes=[ax_th, ax_t])
+    return theta.ireplace_labels(*relabel)
+
+
+# contraction recipes of the effective Hamiltonians, keyed like the branches of the reference's `matvec` methods
+# (mps_common.py:1118-1151 one site, :1321-1348 two sites)
+_ONE_SITE_CHAINS = {
+    ('combined', True): ([('L', 'LHeff', ['(vR.p0*)'], ['(vL.p0)']), ('R', 'RP', ['wL', 'vL'], ['wR', 'vR'])],
+                         (['(vR*.p0)', 'vL*'], ['(vL.p0)', 'vR'])),
+    ('combined', False): ([('R', 'RHeff', ['(p0*.vL)'], ['(p0.vR)']), ('L', 'LP', ['vR', 'wR'], ['vL', 'wL'])],
+                          (['vR*', '(p0.vL*)'], ['vL', '(p0.vR)'])),
+    ('plain', None): ([('L', 'LP', ['vR'], ['vL']), ('L', 'W0', ['wL', 'p0*'], ['wR', 'p0']),
+                       ('R', 'RP', ['wL', 'vL'], ['wR', 'vR'])], (['vR*', 'vL*'], ['vL', 'vR'])),
+}
+_TWO_SITE_CHAINS = {
+    'combined': ([('L', 'LHeff', ['(vR.p0*)'], ['(vL.p0)']), ('R', 'RHeff', ['wL', '(p1*.vL)'], ['wR', '(p1.vR)'])],
+                 (['(vR*.p0)', '(p1.vL*)'], ['(vL.p0)', '(p1.vR)'])),
+    'plain': ([('L', 'LP', ['vR'], ['vL']), ('L', 'W0', ['wL', 'p0*'], ['wR', 'p0']),
+               ('R', 'W1', ['wL', 'p1*'], ['wR', 'p1']), ('R', 'RP', ['wL', 'vL'], ['wR', 'vR'])],
+              (['vR*', 'vL*'], ['vL', 'vR'])),
+}
+
+
 class OneSiteH:
     r"""Effective Hamiltonian ``LP--W0--RP`` acting on the one-site wave function (reference mps_common.py:1040).
 
@@ -38,23 +68,9 @@ class OneSiteH:
 
     def matvec(self, theta):
         """Apply the effective Hamiltonian to `theta` (reference mps_common.py:1118)."""
-        labels = theta.get_leg_labels()
-        if self.combine:
-            if self.move_right:
-                theta = npc.tensordot(self.LHeff, theta, axes=['(vR.p0*)', '(vL.p0)'])     # (vR*.p0) wR vR
-                theta = npc.tensordot(theta, self.RP, axes=[['wR', 'vR'], ['wL', 'vL']])
-                theta.ireplace_labels(['(vR*.p0)', 'vL*'], ['(vL.p0)', 'vR'])
-            else:
-                theta = npc.tensordot(theta, self.RHeff, axes=['(p0.vR)', '(p0*.vL)'])     # vL wL (p0.vL*)
-                theta = npc.tensordot(self.LP, theta, axes=[['vR', 'wR'], ['vL', 'wL']])
-                theta.ireplace_labels(['vR*', '(p0.vL*)'], ['vL', '(p0.vR)'])
-        else:
-            theta = npc.tensordot(self.LP, theta, axes=['vR', 'vL'])
-            theta = npc.tensordot(self.W0, theta, axes=[['wL', 'p0*'], ['wR', 'p0']])
-            theta = npc.tensordot(theta, self.RP, axes=[['wR', 'vR'], ['wL', 'vL']])
-            theta.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
-        theta.itranspose(labels)
-        return theta
+        key = ('combined', bool(self.move_right)) if self.combine else ('plain', None)
+        chain, relabel = _ONE_SITE_CHAINS[key]
+        return _apply_chain(self, theta, chain, relabel).itranspose(theta.get_leg_labels())
 
     def combine_Heff(self, env):
         """Reference mps_common.py:1152."""
@@ -173,18 +189,8 @@ class TwoSiteH:
         labels = theta.get_leg_labels()
         if self.combine and self._use_split(theta):
             return self._matvec_split(theta, labels)
-        if self.combine:
-            theta = npc.tensordot(self.LHeff, theta, axes=['(vR.p0*)', '(vL.p0)'])
-            theta = npc.tensordot(theta, self.RHeff, axes=[['wR', '(p1.vR)'], ['wL', '(p1*.vL)']])
-            theta.ireplace_labels(['(vR*.p0)', '(p1.vL*)'], ['(vL.p0)', '(p1.vR)'])
-        else:
-            theta = npc.tensordot(self.LP, theta, axes=['vR', 'vL'])
-            theta = npc.tensordot(self.W0, theta, axes=[['wL', 'p0*'], ['wR', 'p0']])
-            theta = npc.tensordot(theta, self.W1, axes=[['wR', 'p1'], ['wL', 'p1*']])
-            theta = npc.tensordot(theta, self.RP, axes=[['wR', 'vR'], ['wL', 'vL']])
-            theta.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
-        theta.itranspose(labels)
-        return theta
+        chain, relabel = _TWO_SITE_CHAINS['combined' if self.combine else 'plain']
+        return _apply_chain(self, theta, chain, relabel).itranspose(labels)
 
     def _use_split(self, theta):
         if self.matvec_order == 'auto':
@@ -337,35 +343,27 @@ class Mixer:
             return self.mixed_svd_2site(engine, theta, i0, mix_left, mix_right, qtotal_LR)
         except NotImplementedError:
             pass
-        if mix_left and mix_right:
-            qtotal_L, qtotal_R = self.determine_qtotal_L_R(theta.qtotal, qtotal_LR)
-            theta_L = theta.replace_label('(p1.vR)', 'vR')
-            U, _, _, err_L = self.mix_and_decompose_1site(engine, theta_L, i0, move_right=True)
-            U = U.gauge_total_charge(1, qtotal_L)
-            theta_R = theta.replace_labels(['(vL.p0)', '(p1.vR)'], ['vL', '(p0.vR)'])
-            _, S_approx, VH, err_R = self.mix_and_decompose_1site(engine, theta_R, i0 + 1, move_right=False)
-            VH = VH.gauge_total_charge(0, qtotal_R)
-            VH.ireplace_label('(p0.vR)', '(p1.vR)')
-            theta = npc.tensordot(U.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)'])
-            theta = npc.tensordot(theta, VH.conj(), axes=['(p1.vR)', '(p1*.vR*)'])
-            theta.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
-            theta = theta / theta.norm()
-            S = theta
-            err = err_L + err_R
-        elif mix_left:
-            theta_L = theta.replace_label('(p1.vR)', 'vR')
-            U, S, VH, err = self.mix_and_decompose_1site(engine, theta_L, i0, move_right=True)
-            VH.ireplace_label('vR', '(p1.vR)')
-            S_approx = S
-        elif mix_right:
-            theta_R = theta.replace_labels(['(vL.p0)', '(p1.vR)'], ['vL', '(p0.vR)'])
-            U, S, VH, err = self.mix_and_decompose_1site(engine, theta_R, i0 + 1, move_right=False)
-            U.ireplace_label('vL', '(vL.p0)')
-            VH.ireplace_label('(p0.vR)', '(p1.vR)')
-            S_approx = S
-        else:
+        if not (mix_left or mix_right):
             raise ValueError('Expected mix_left=True and/or mix_right=True.')
-        return U, S, VH, err, S_approx
+        # view the two-site theta as a one-site wave function whose second / first leg is an opaque virtual leg
+        as_left = theta.replace_label('(p1.vR)', 'vR')
+        as_right = theta.replace_labels(['(vL.p0)', '(p1.vR)'], ['vL', '(p0.vR)'])
+        if mix_left and not mix_right:
+            U, S, VH, err = self.mix_and_decompose_1site(engine, as_left, i0, move_right=True)
+            return U, S, VH.ireplace_label('vR', '(p1.vR)'), err, S
+        if mix_right and not mix_left:
+            U, S, VH, err = self.mix_and_decompose_1site(engine, as_right, i0 + 1, move_right=False)
+            return U.ireplace_label('vL', '(vL.p0)'), S, VH.ireplace_label('(p0.vR)', '(p1.vR)'), err, S
+        # both sides: two independent expansions, the bond matrix is what remains of theta between the two isometries
+        qtotal_L, qtotal_R = self.determine_qtotal_L_R(theta.qtotal, qtotal_LR)
+        U, _, _, err_L = self.mix_and_decompose_1site(engine, as_left, i0, move_right=True)
+        _, S_approx, VH, err_R = self.mix_and_decompose_1site(engine, as_right, i0 + 1, move_right=False)
+        U = U.gauge_total_charge(1, qtotal_L)
+        VH = VH.gauge_total_charge(0, qtotal_R).ireplace_label('(p0.vR)', '(p1.vR)')
+        bond = npc.tensordot(U.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)'])
+        bond = npc.tensordot(bond, VH.conj(), axes=['(p1.vR)', '(p1*.vR*)'])
+        bond.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
+        return U, bond / bond.norm(), VH, err_L + err_R, S_approx
 
     @staticmethod
     def determine_qtotal_L_R(theta_qtotal, qtotal_LR):

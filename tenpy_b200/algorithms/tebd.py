@@ -243,58 +243,52 @@ class QRBasedTEBDEngine(TEBDEngine):
         chi = min(np.shape(self.psi.get_SL(i)))
         return max(expand_0 - chi / chi_max * (expand_0 - expand), expand)
 
-    def update_bond(self, i, U_bond):
-        """Reference tebd.py:681."""
-        i0, i1 = i - 1, i
-        expand = self._expansion_rate(i)
-        C = self.psi.get_theta(i0, n=2, formL=0.)
+    def _two_site_theta(self, i0, U_bond, with_left_S):
+        """`U_bond` applied to sites ``(i0, i0+1)``; returns ``(C, theta)``: `C` without, `theta` (combined to a
+        matrix) with the Schmidt values on the left bond (`C` is None for ``with_left_S=True``)."""
+        C = self.psi.get_theta(i0, n=2, formL=1. if with_left_S else 0.)
         C = npc.tensordot(U_bond, C, axes=(['p0*', 'p1*'], ['p0', 'p1']))
         C.itranspose(['vL', 'p0', 'p1', 'vR'])
-        theta = C.scale_axis(self.psi.get_SL(i0), 'vL')
+        theta = C if with_left_S else C.scale_axis(self.psi.get_SL(i0), 'vL')
         theta = theta.combine_legs([('vL', 'p0'), ('p1', 'vR')], qconj=[+1, -1])
-        old_B_L = self.psi.get_B(i0, 'B')
-        old_B_R = self.psi.get_B(i1, 'B')
-        _, S, B_R, form, trunc_err, renormalize = decompose_theta_qr_based(
-            old_qtotal_L=old_B_L.qtotal, old_qtotal_R=old_B_R.qtotal, old_bond_leg=old_B_R.get_leg('vL'), theta=theta,
-            move_right=False, expand=expand, min_block_increase=self.options.get('cbe_min_block_increase', 1),
-            use_eig_based_svd=self.options.get('use_eig_based_svd', False), trunc_params=self.trunc_params,
-            compute_err=self.options.get('compute_err', True), return_both_T=False)
-        assert form[1] == 'B'
-        B_L = npc.tensordot(C.combine_legs(('p1', 'vR'), pipes=theta.legs[1]), B_R.conj(),
-                            axes=['(p1.vR)', '(p*.vR*)'])
-        B_L = B_L / renormalize
-        B_L.ireplace_labels(['p0', 'vL*'], ['p', 'vR'])
-        B_R = B_R.split_legs(1)
+        return (None if with_left_S else C), theta
+
+    def _qr_split(self, i0, theta, both, eig_ok=True):
+        """:func:`decompose_theta_qr_based` of `theta` on bond ``(i0, i0+1)`` with this engine's options."""
+        old_L, old_R = self.psi.get_B(i0, 'B'), self.psi.get_B(i0 + 1, 'B')
+        use_eig = self.options.get('use_eig_based_svd', False)
+        if use_eig and not eig_ok:
+            raise NotImplementedError('update_bond_imag does not (yet) support eig based SVD')
+        return decompose_theta_qr_based(
+            old_qtotal_L=old_L.qtotal, old_qtotal_R=old_R.qtotal, old_bond_leg=old_R.get_leg('vL'), theta=theta,
+            move_right=False, expand=self._expansion_rate(i0 + 1),
+            min_block_increase=self.options.get('cbe_min_block_increase', 1), use_eig_based_svd=use_eig,
+            trunc_params=self.trunc_params, compute_err=self.options.get('compute_err', True), return_both_T=both)
+
+    def _store(self, i0, left, left_form, S, B_R, renormalize, trunc_err):
         self.psi.norm *= renormalize
-        self.psi.set_B(i0, B_L, form='B')
-        self.psi.set_SL(i1, S)
-        self.psi.set_B(i1, B_R, form='B')
-        self._trunc_err_bonds[i] = self._trunc_err_bonds[i] + trunc_err
+        self.psi.set_B(i0, left, form=left_form)
+        self.psi.set_SL(i0 + 1, S)
+        self.psi.set_B(i0 + 1, B_R.split_legs(1), form='B')
+        self._trunc_err_bonds[i0 + 1] = self._trunc_err_bonds[i0 + 1] + trunc_err
         return trunc_err
 
+    def update_bond(self, i, U_bond):
+        """Unitary-style update keeping both sites in 'B' form (reference tebd.py:681): only the right isometry comes
+        out of the QR based split, ``B_L = C . B_R^dagger`` avoids dividing by small Schmidt values."""
+        i0 = i - 1
+        C, theta = self._two_site_theta(i0, U_bond, with_left_S=False)
+        _, S, B_R, form, trunc_err, renormalize = self._qr_split(i0, theta, both=False)
+        assert form[1] == 'B'
+        B_L = npc.tensordot(C.combine_legs(('p1', 'vR'), pipes=theta.legs[1]), B_R.conj(),
+                            axes=['(p1.vR)', '(p*.vR*)']) / renormalize
+        B_L.ireplace_labels(['p0', 'vL*'], ['p', 'vR'])
+        return self._store(i0, B_L, 'B', S, B_R, renormalize, trunc_err)
+
     def update_bond_imag(self, i, U_bond):
-        """Reference tebd.py:741."""
-        i0, i1 = i - 1, i
-        expand = self._expansion_rate(i)
-        theta = self.psi.get_theta(i0, n=2)
-        theta = npc.tensordot(U_bond, theta, axes=(['p0*', 'p1*'], ['p0', 'p1']))
-        theta.itranspose(['vL', 'p0', 'p1', 'vR'])
-        theta = theta.combine_legs([('vL', 'p0'), ('p1', 'vR')], qconj=[+1, -1])
-        old_B_L = self.psi.get_B(i0, 'B')
-        old_B_R = self.psi.get_B(i1, 'B')
-        if self.options.get('use_eig_based_svd', False):
-            raise NotImplementedError('update_bond_imag does not (yet) support eig based SVD')
-        A_L, S, B_R, form, trunc_err, renormalize = decompose_theta_qr_based(
-            old_qtotal_L=old_B_L.qtotal, old_qtotal_R=old_B_R.qtotal, old_bond_leg=old_B_R.get_leg('vL'), theta=theta,
-            move_right=False, expand=expand, min_block_increase=self.options.get('cbe_min_block_increase', 1),
-            use_eig_based_svd=False, trunc_params=self.trunc_params,
-            compute_err=self.options.get('compute_err', True), return_both_T=True)
+        """Non-unitary update leaving ``A S B`` around the bond (reference tebd.py:741)."""
+        i0 = i - 1
+        _, theta = self._two_site_theta(i0, U_bond, with_left_S=True)
+        A_L, S, B_R, form, trunc_err, renormalize = self._qr_split(i0, theta, both=True, eig_ok=False)
         assert form == ['A', 'B']
-        A_L = A_L.split_legs(0)
-        B_R = B_R.split_legs(1)
-        self.psi.norm *= renormalize
-        self.psi.set_B(i0, A_L, form='A')
-        self.psi.set_SL(i1, S)
-        self.psi.set_B(i1, B_R, form='B')
-        self._trunc_err_bonds[i] = self._trunc_err_bonds[i] + trunc_err
-        return trunc_err
+        return self._store(i0, A_L.split_legs(0), 'A', S, B_R, renormalize, trunc_err)

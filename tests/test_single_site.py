@@ -127,7 +127,36 @@ def _check_subspace_expansion():
         assert list(psi.chi) == list(g[key + '_chi']), key
 
 
+def _check_mix_both_sides():
+    """Mixer.mix_and_decompose_2site with both bonds mixed (reference mps_common.py:1770-1785; the infinite-DMRG case):
+    both factors are isometries, U . S . VH reproduces theta up to the truncation"""
+    from tenpy_b200.models import SpinChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import SubspaceExpansion
+    from tenpy_b200.linalg import np_conserved as npc
+    L = 8
+    M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 0.8, 'conserve': 'Sz'})
+    psi = MPS.from_product_state(M.lat_sites, ['up', 'down'] * (L // 2))
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': True, 'trunc_params': {'chi_max': 40, 'svd_min': 1e-14}})
+    eng.sweep()
+    eng.sweep()
+    eng.i0, eng.move_right, eng.update_LP_RP = 3, True, (True, True)
+    theta = eng.prepare_update_local()
+    mixer = SubspaceExpansion({'amplitude': 1e-6})
+    qL = psi.get_B(3, form=None).qtotal
+    U, S, VH, err, S_a = mixer.mix_and_decompose_2site(eng, theta, 3, True, True, [qL, theta.qtotal - qL])
+    iso = npc.tensordot(U.conj(), U, axes=['(vL*.p0*)', '(vL.p0)']).to_ndarray()
+    assert np.max(np.abs(iso - np.eye(len(iso)))) < 1e-11
+    iso = npc.tensordot(VH, VH.conj(), axes=['(p1.vR)', '(p1*.vR*)']).to_ndarray()
+    assert np.max(np.abs(iso - np.eye(len(iso)))) < 1e-11
+    rec = npc.tensordot(npc.tensordot(U, S, axes=['vR', 'vL']), VH, axes=['vR', 'vL'])
+    ov = abs(npc.inner(rec, theta, axes='range', do_conj=True)) / (npc.norm(rec) * npc.norm(theta))
+    assert abs(ov - 1.) < 1e-9 and abs(npc.norm(S) - 1.) < 1e-12
+
+
 def test_subspace_expansion_host_logic(fake_device):
+    _check_mix_both_sides()
     _check_subspace_expansion()
 
 
