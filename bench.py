@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument('--cpu-bonds', type=int, default=2, help='bond updates per CPU sample')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-blocksparse', action='store_true', help='skip the configs[2]/[3] shaped matvec probes')
     return ap.parse_args()
 
 
@@ -367,6 +368,7 @@ def run_b200(args):
     roof = kernel_probes(lib, chi, d, D)
     mv_orders = matvec_order_probe(eng, psi, L, chi, d, D)
     roof['svd']['workload_theta'] = svd_theta_probe(eng, psi, L)
+    bs_probes = blocksparse_probes(small=(chi < 256)) if not args.no_blocksparse else None
 
     # ---- gather over ranks
     stats = torch.tensor([ms, E_final, S_mid, e2e['value'] if e2e else 0.], dtype=torch.float64, device=lib.device)
@@ -398,7 +400,8 @@ def run_b200(args):
             'config': workload_config(args, world), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'roofline_gemm': roof['gemm'], 'roofline_svd': roof['svd'],
             'kernel_time_shares': shares, 'kernel_family_ms_per_sweep': {k: round(v[1], 2) for k, v in prof.items()},
-            'matvec_orders': mv_orders, 'matvec_gflops': _matvec_gflops(mv_orders), 'peaks': peaks_kind,
+            'matvec_orders': mv_orders, 'matvec_gflops': _matvec_gflops(mv_orders),
+            'blocksparse_matvec': bs_probes, 'peaks': peaks_kind,
             'result': {'E': [float(x) for x in allst[:, 1]], 'S_mid': [float(x) for x in allst[:, 2]],
                        'N_lanczos_mean': N_lan, 'svd_jacobi_sweeps_mean': float(np.mean(jsw)),
                        'svd_jacobi_sweeps_max': int(np.max(jsw)), 'svd_calls': svd_stats['calls'],
@@ -491,6 +494,78 @@ def svd_theta_probe(eng, psi, L, reps=3):
                 'rank_above_1e-10': int(np.sum(S > 1e-10 * S.max())), 'rank_above_1e-8': int(np.sum(S > 1e-8 * S.max()))}
     except Exception as e:  # a probe must never lose the bench line
         return {'error': repr(e)}
+
+
+def blocksparse_probes(small=False):
+    """effective-H matvec (LHeff . theta . RHeff) on synthetic random-charge Arrays of the BASELINE.json configs[2] / [3]
+    shapes (generator modelled on the reference's tests/benchmark/tensordot_npc.py:36-51):
+    U(1) chi=1024 d=2 D=5 (XXZ-like) and U(1)xU(1) chi=2048 d=4 D=6 (Hubbard-like).  Reports GEMMs per matvec, executed
+    flops (sum 2 m k n over the block products) and ms per matvec (CUDA events).  These shapes are launch / latency bound
+    (two grouped launches per matvec), not flop bound."""
+    import torch
+    from tenpy_b200.linalg import np_conserved as npc
+    from tenpy_b200.linalg.charges import ChargeInfo, LegCharge
+    out = []
+    cases = [('xxz_like', 1024, 12), ('hubbard_like', 2048, 40)] if not small else [('xxz_like', 32, 4), ('hubbard_like', 32, 6)]
+    for kind, chi, nsec in cases:
+        try:
+            rng = np.random.default_rng(0)
+            if kind == 'xxz_like':
+                ci = ChargeInfo([1], ['2*Sz'])
+                p = LegCharge.from_qflat(ci, [[-1], [1]], +1)
+                wq, spread = np.array([[0], [2], [-2], [0], [0]]), 16
+            else:
+                ci = ChargeInfo([1, 1], ['N', '2*Sz'])
+                p = LegCharge.from_qflat(ci, [[0, 0], [1, -1], [1, 1], [2, 0]], +1)
+                wq, spread = np.array([[0, 0], [1, 1], [-1, -1], [1, -1], [-1, 1], [0, 0]]), 8
+
+            def sector_leg(qconj):
+                cuts = np.sort(rng.choice(np.arange(1, chi), size=nsec - 1, replace=False))
+                charges = set()
+                while len(charges) < nsec:
+                    charges.add(tuple(int(x) for x in rng.integers(-spread, spread + 1, size=ci.qnumber)))
+                charges = np.array(sorted(charges))
+                charges = charges[np.lexsort(charges.T)]
+                return LegCharge.from_qind(ci, np.concatenate(([0], cuts, [chi])), charges, qconj)
+            D = len(wq)
+            vL, vR = sector_leg(+1), sector_leg(-1)
+            w = LegCharge.from_qind(ci, np.arange(D + 1), wq, -1)
+            gen = rng.standard_normal
+            L4 = npc.Array.from_func(gen, [vL, p, w, vL.conj(), p.conj()], labels=['vR*', 'p0', 'wR', 'vR', 'p0*'])
+            LHeff = L4.combine_legs([['vR*', 'p0'], ['vR', 'p0*']], qconj=[+1, -1], new_axes=[0, 2])
+            R4 = npc.Array.from_func(gen, [w.conj(), p.conj(), vR.conj(), p, vR], labels=['wL', 'p1*', 'vL', 'p1', 'vL*'])
+            RHeff = R4.combine_legs([['p1', 'vL*'], ['p1*', 'vL']], qconj=[-1, +1], new_axes=[2, 1])
+            del L4, R4
+            theta = npc.Array.from_func(gen, [LHeff.get_leg('(vR.p0*)').conj(), RHeff.get_leg('(p1*.vL)').conj()],
+                                        labels=['(vL.p0)', '(p1.vR)'])
+
+            def mv(th):
+                t = npc.tensordot(LHeff, th, axes=['(vR.p0*)', '(vL.p0)'])
+                return npc.tensordot(t, RHeff, axes=[['wR', '(p1.vR)'], ['wL', '(p1*.vL)']])
+            n_plans0 = set(npc._PLAN_CACHE.keys())
+            for _ in range(3):
+                mv(theta)
+            new = [v for k, v in npc._PLAN_CACHE.items() if k not in n_plans0]
+            flops = float(sum(v[2].flops for v in new))
+            ngemm = int(sum(v[2].n_pairs for v in new))
+            reps = 20
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                mv(theta)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / reps
+            out.append({'case': kind, 'chi': chi, 'd': int(p.ind_len), 'D': D, 'n_sectors': nsec,
+                        'blocks': {'LHeff': LHeff.stored_blocks, 'theta': theta.stored_blocks, 'RHeff': RHeff.stored_blocks},
+                        'gemms_per_matvec': ngemm, 'flop_per_matvec': flops,
+                        'dense_equivalent_flop': 4. * D * p.ind_len**3 * float(chi)**3, 'ms_per_matvec': ms,
+                        'gflops': flops / ms / 1e6 if ms > 0 else None})
+            del LHeff, RHeff, theta
+        except Exception as e:  # a probe must never lose the bench line
+            out.append({'case': kind, 'error': repr(e)})
+    return out
 
 
 def kernel_probes(lib, chi, d, D):
