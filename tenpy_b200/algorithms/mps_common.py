@@ -202,7 +202,7 @@ class TwoSiteH:
         """``LP . theta . (W0 W1) . RP`` on the split legs; interface (labels, pipes) of the combined matvec."""
         if self._W01 is None:
             self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])   # wL p0 p0* p1 p1* wR  (D^2 d^4 numbers)
-        th = theta.split_legs(['(vL.p0)', '(p1.vR)'])                        # vL p0 p1 vR
+        th = theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)            # vL p0 p1 vR (read only here)
         th = npc.tensordot(self.LP, th, axes=['vR', 'vL'])                   # vR* wR p0 p1 vR      2 D d^2 chi^3
         fused = self._apply_W01_fused(th) if self.mpo_apply == 'fused' else None
         if fused is not None:
@@ -211,7 +211,7 @@ class TwoSiteH:
             th = npc.tensordot(th, self._W01, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])  # vR* vR p0 p1 wR
             th = npc.tensordot(th, self.RP, axes=[['vR', 'wR'], ['vL', 'wL']])   # vR* p0 p1 vL*   2 D d^2 chi^3
         th.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
-        th = th.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR])
+        th = th.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)  # th is ours
         return th.itranspose(labels)
 
     def _apply_W01_fused(self, th):

@@ -631,8 +631,11 @@ class Array:
         kwargs.setdefault('qconj', legs[0].qconj)
         return LegPipe(legs, **kwargs)
 
-    def combine_legs(self, combine_legs, new_axes=None, pipes=None, qconj=None):
-        """Reshape: fuse bundles of legs into pipes (reference npc:1561; worker npc:4404 / pyx:1013)."""
+    def combine_legs(self, combine_legs, new_axes=None, pipes=None, qconj=None, _view=False):
+        """Reshape: fuse bundles of legs into pipes (reference npc:1561; worker npc:4404 / pyx:1013).
+
+        ``_view=True`` (internal): if the move is a pure relabelling of the packed buffer, share it instead of
+        copying -- only for callers that own `self` or treat the result as read-only."""
         combine_legs = list(combine_legs)
         if len(combine_legs) and not isinstance(combine_legs[0], (list, tuple, np.ndarray)):
             combine_legs = [combine_legs]
@@ -704,13 +707,16 @@ class Array:
             cached = (new_layout, rec, backend.to_device(rec), pipes)
             lay.cache[key] = cached
         new_layout, rec, rec_dev = cached[:3]
+        if _view and new_layout.size == lay.size and int(rec[0, 2]) == int(lay.sizes.sum()) and _is_identity_move(rec):
+            return res._set_blocks(new_layout, self._buf)
         buf = _dest_buffer(new_layout, rec)
         backend.get_lib().copy_blocks(rec, rec_dev, self._buf, buf)
         res._set_blocks(new_layout, buf)
         return res
 
-    def split_legs(self, axes=None, cutoff=0.):
-        """Reshape: split pipes into their incoming legs (reference npc:1707; worker npc:4483 / pyx:1136)."""
+    def split_legs(self, axes=None, cutoff=0., _view=False):
+        """Reshape: split pipes into their incoming legs (reference npc:1707; worker npc:4483 / pyx:1136).
+        ``_view``: see :meth:`combine_legs`."""
         if axes is None:
             axes = [i for i, l in enumerate(self.legs) if isinstance(l, LegPipe)]
         elif not isinstance(axes, (list, tuple, np.ndarray)):
@@ -748,6 +754,8 @@ class Array:
             cached = (new_layout, rec, backend.to_device(rec))
             lay.cache[key] = cached
         new_layout, rec, rec_dev = cached
+        if _view and new_layout.size == lay.size and int(rec[0, 2]) == int(lay.sizes.sum()) and _is_identity_move(rec):
+            return res._set_blocks(new_layout, self._buf)
         buf = _dest_buffer(new_layout, rec)
         backend.get_lib().copy_blocks(rec, rec_dev, self._buf, buf)
         res._set_blocks(new_layout, buf)
@@ -1081,6 +1089,15 @@ def tensordot(a, b, axes=2):
     plan.run(a._buf, b._buf, buf)
     res._set_blocks(lay_c, buf)
     return res
+
+
+def _is_identity_move(rec):
+    """True if the copy records describe ONE contiguous block copied onto the same offsets (a pure relabelling of the
+    packed buffer, e.g. combining / splitting legs of an Array without charges)."""
+    if len(rec) != 1 or rec[0, 0] != 0 or rec[0, 1] != 0:
+        return False
+    r = int(rec[0, 3])
+    return bool(np.all(rec[0, 10:10 + r] == rec[0, 16:16 + r]))
 
 
 def _dest_buffer(layout, rec):

@@ -374,3 +374,43 @@ def test_lanczos_device_scalars(fake_device):
                                          'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
     assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
     assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
+
+
+def test_split_matvec_shares_buffers_without_charges(fake_device):
+    """the split-order matvec relabels instead of copying when combining / splitting is the identity on the packed buffer
+    (no charges): no block-move launch for the theta reshapes, input untouched, result owns its buffer"""
+    from tenpy_b200.models import TFIChain, SpinChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg import np_conserved as npc
+    M = TFIChain({'L': 8, 'J': 1., 'g': 1.1, 'conserve': None})
+    psi = MPS.from_product_state(M.lat_sites, ['up'] * 8)
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': None, 'combine': True, 'trunc_params': {'chi_max': 24, 'svd_min': 1e-12}})
+    eng.sweep()
+    eng.sweep()
+    H = TwoSiteH(eng.env, 3, combine=True, matvec_order='split')
+    theta = H.combine_theta(psi.get_theta(3, 2))
+    before = theta.to_ndarray().copy()
+    H.matvec(theta)                                   # plans cached now
+    n0 = fake_device.calls.get('copy_blocks', 0)
+    out = H.matvec(theta)
+    n_copies = fake_device.calls.get('copy_blocks', 0) - n0
+    ref = TwoSiteH(eng.env, 3, combine=True, matvec_order='combined').matvec(theta)
+    assert npc.norm(out - ref) < 1e-13 * npc.norm(ref)
+    assert np.array_equal(theta.to_ndarray(), before)
+    assert out._buf.data_ptr() != theta._buf.data_ptr()
+    # the two reshapes of theta are views now: only the transpositions inside the three contractions are left
+    view_th = theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)
+    assert view_th._buf.data_ptr() == theta._buf.data_ptr()
+    assert theta.split_legs(['(vL.p0)', '(p1.vR)'])._buf.data_ptr() != theta._buf.data_ptr()
+    assert n_copies <= 4
+    # with charges the reshapes move blocks: never a view
+    M = SpinChain({'L': 8, 'Jx': 1., 'Jy': 1., 'Jz': 1., 'conserve': 'Sz'})
+    psi = MPS.from_product_state(M.lat_sites, ['up', 'down'] * 4)
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': True, 'combine': True, 'trunc_params': {'chi_max': 16, 'svd_min': 1e-12}})
+    eng.sweep()
+    H = TwoSiteH(eng.env, 3, combine=True, matvec_order='split')
+    theta = H.combine_theta(psi.get_theta(3, 2))
+    if theta.stored_blocks > 1:
+        assert theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)._buf.data_ptr() != theta._buf.data_ptr()
