@@ -241,14 +241,45 @@ class TwoSiteH:
         return res._set_blocks(lay, buf)
 
     def combine_Heff(self, env, left=True, right=True):
-        """Reference mps_common.py:1350."""
+        """Reference mps_common.py:1350.  The pipes are made from the legs right away; the contractions
+        ``LHeff = LP.W0`` / ``RHeff = W1.RP`` (each a ``D (d chi)^2`` tensor) are deferred to their first use
+        (properties `LHeff` / `RHeff`): with the split-order matvec and no mixer only the side the sweep moves away
+        from is ever needed (`update_LP` / `update_RP`)."""
         if left:
-            self.LHeff = env._contract_LHeff(self.i0, 'p0')
-            self.pipeL = self.LHeff.get_leg('(vR*.p0)')
+            self._LHeff = None
+            self.pipeL = npc.LegPipe([self.LP.get_leg('vR*'), self.W0.get_leg('p0')], qconj=+1)
         if right:
-            self.RHeff = env._contract_RHeff(self.i0 + 1, 'p1')
-            self.pipeR = self.RHeff.get_leg('(p1.vL*)')
+            self._RHeff = None
+            self.pipeR = npc.LegPipe([self.W1.get_leg('p1'), self.RP.get_leg('vL*')], qconj=-1)
         self.acts_on = ['(vL.p0)', '(p1.vR)']
+
+    @property
+    def LHeff(self):
+        if not self.combine:
+            raise AttributeError('LHeff is only defined for combine=True')
+        if self._LHeff is None:
+            t = npc.tensordot(self.LP, self.W0, axes=['wR', 'wL'])           # as MPOEnvironment._contract_LHeff
+            self._LHeff = t.combine_legs([['vR*', 'p0'], ['vR', 'p0*']], pipes=[self.pipeL, self.pipeL.conj()],
+                                         new_axes=[0, 2])
+        return self._LHeff
+
+    @LHeff.setter
+    def LHeff(self, value):
+        self._LHeff = value
+
+    @property
+    def RHeff(self):
+        if not self.combine:
+            raise AttributeError('RHeff is only defined for combine=True')
+        if self._RHeff is None:
+            t = npc.tensordot(self.W1, self.RP, axes=['wR', 'wL'])           # as MPOEnvironment._contract_RHeff
+            self._RHeff = t.combine_legs([['p1', 'vL*'], ['p1*', 'vL']], pipes=[self.pipeR, self.pipeR.conj()],
+                                         new_axes=[2, 1])
+        return self._RHeff
+
+    @RHeff.setter
+    def RHeff(self, value):
+        self._RHeff = value
 
     def combine_theta(self, theta):
         """Reference mps_common.py:1374."""

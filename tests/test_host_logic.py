@@ -400,6 +400,9 @@ def test_split_matvec_shares_buffers_without_charges(fake_device):
     assert npc.norm(out - ref) < 1e-13 * npc.norm(ref)
     assert np.array_equal(theta.to_ndarray(), before)
     assert out._buf.data_ptr() != theta._buf.data_ptr()
+    # LHeff / RHeff are contracted on first use only: the split matvec needs neither
+    assert H._LHeff is None and H._RHeff is None
+    assert H.LHeff.get_leg_labels() == ['(vR*.p0)', 'wR', '(vR.p0*)'] and H._RHeff is None
     # the two reshapes of theta are views now: only the transpositions inside the three contractions are left
     view_th = theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)
     assert view_th._buf.data_ptr() == theta._buf.data_ptr()
