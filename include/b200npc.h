@@ -157,6 +157,15 @@ int b200_take_blocks_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t
 int b200_scale_axis_f64(int64_t n_tasks, const int64_t *task_dev, const int64_t *task_host,
                         const double *S_dev, double *X, b200_stream_t stream);
 
+/* Batched Householder QR: block i is A_i (m_i x n_i, row-major at A + a_off[i]); Q_i (m_i x k_i, k = min(m, n)) is
+ * written to Q + q_off[i], R_i (k_i x n_i, upper triangular, non-negative diagonal) to R + r_off[i].  One CTA per block,
+ * one launch, no host round trip.  replaces the per-block np.linalg.qr of npc.qr (np_conserved.py:4139).  `work` =
+ * device scratch of b200_block_qr_worksize bytes.  Opt-in (np_conserved.qr_method) until timed on the GPU. */
+int64_t b200_block_qr_worksize(int64_t nblocks, const int64_t *m_host, const int64_t *n_host);
+int b200_block_qr_f64(int64_t nblocks, const int64_t *m_host, const int64_t *n_host, const int64_t *a_off_host,
+                      const int64_t *q_off_host, const int64_t *r_off_host, const double *A, double *Q, double *R,
+                      void *work, int64_t work_bytes, b200_stream_t stream);
+
 /* OUT[o, n, i] = sum_k M[n, k] T[o, k, i]  (T: outer x K x inner, OUT: outer x N x inner, row-major, i contiguous;
  * M: N x K on the device, K <= 32): a small matrix applied to the middle index without changing the layout.  Fuses the
  * two block transpositions and the skinny GEMM npc.tensordot needs for "W0.W1 applied to LP.theta" in the split-order

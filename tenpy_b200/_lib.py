@@ -61,6 +61,8 @@ _SIGNATURES = {
     'b200_take_blocks_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp, c_vp]),
     'b200_scale_axis_f64': (ctypes.c_int, [c_i64, c_vp, c_i64p, c_vp, c_vp, c_vp]),
     'b200_col_sqnorms_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'b200_block_qr_worksize': (c_i64, [c_i64, c_i64p, c_i64p]),
+    'b200_block_qr_f64': (ctypes.c_int, [c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b200_mid_contract_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'b200_svd_set_deflation': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_eig_variant': (ctypes.c_int, [ctypes.c_int]),
@@ -322,6 +324,16 @@ class DeviceLib:
                                                   nact.ctypes.data_as(c_i32p), transp.ctypes.data_as(c_i32p),
                                                   self.stream()))
         return info, nact, transp
+
+    def block_qr(self, m, n, a_off, q_off, r_off, A, Q, R):
+        """batched Householder QR of the blocks (include/b200npc.h)"""
+        ms, ns, ao, qo, ro = [_i64(x) for x in (m, n, a_off, q_off, r_off)]
+        nb = len(ms[0])
+        wbytes = int(self.c.b200_block_qr_worksize(nb, ms[1], ns[1]))
+        work = self.torch.empty(wbytes, dtype=self.torch.uint8, device=self.device)
+        with _Prof(self, 'svd'):
+            self._check(self.c.b200_block_qr_f64(nb, ms[1], ns[1], ao[1], qo[1], ro[1], _ptr(A), _ptr(Q), _ptr(R),
+                                                 _ptr(work), wbytes, self.stream()))
 
     def col_sqnorms(self, rows, cols, ld, X, OUT):
         with _Prof(self, 'svd'):

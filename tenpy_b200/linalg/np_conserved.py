@@ -1471,6 +1471,9 @@ def _fill_null_vectors(lib, m, n, k, r, kf, transposed, bufU, u_off, bufV, v_off
 
 
 qr_stats = {'calls': 0, 'columns': 0, 'replaced': 0}   # diagnostics of the Gram-Schmidt QR
+# 'cgs2': Gram-Schmidt on the GEMM / BLAS-1 kernels (GPU-verified building blocks, one host round trip per column);
+# 'householder': b200_block_qr_f64, one launch for all blocks (host-checked, opt-in until it has run on a GPU)
+qr_method = 'cgs2'
 
 
 def _block_qr_cgs2(lib, m, n, A, Q, R):
@@ -1586,11 +1589,14 @@ def qr(a, mode='reduced', inner_labels=[None, None], cutoff=None, pos_diag_R=Fal
         bufQ = backend.zeros(lay_Q.size)
         bufR = backend.zeros(lay_R.size)
         lib = backend.get_lib()
-        for b in range(lay.nblocks):
-            mb, nb, kb = int(m[b]), int(n[b]), int(k[b])
-            ao = int(lay.offsets[b])
-            _block_qr_cgs2(lib, mb, nb, a._buf[ao:ao + mb * nb], bufQ[int(q_off[b]):int(q_off[b]) + mb * kb],
-                           bufR[int(r_off[b]):int(r_off[b]) + kb * nb])
+        if qr_method == 'householder':
+            lib.block_qr(m, n, lay.offsets, q_off, r_off, a._buf, bufQ, bufR)
+        else:
+            for b in range(lay.nblocks):
+                mb, nb, kb = int(m[b]), int(n[b]), int(k[b])
+                ao = int(lay.offsets[b])
+                _block_qr_cgs2(lib, mb, nb, a._buf[ao:ao + mb * nb], bufQ[int(q_off[b]):int(q_off[b]) + mb * kb],
+                               bufR[int(r_off[b]):int(r_off[b]) + kb * nb])
         Q._set_blocks(lay_Q, bufQ)
         R._set_blocks(lay_R, bufR)
         qr_stats['calls'] += 1

@@ -49,6 +49,28 @@ def main():
                                                                             npc.svd_stats['jacobi_sweeps'][-1]))
         finally:
             lib.svd_set_eig_variant(old)
+    # Householder block QR (b200_block_qr_f64) against the Gram-Schmidt route and numpy
+    for shape in [(7, 4), (4, 7), (64, 64), (300, 130), (512, 512)]:
+        A = rng.standard_normal(shape)
+        a = npc.Array.from_ndarray_trivial(A)
+        res = {}
+        for method in ('cgs2', 'householder'):
+            old_m = npc.qr_method
+            npc.qr_method = method
+            try:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                Q, R = npc.qr(a)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) * 1e3
+            finally:
+                npc.qr_method = old_m
+            q, r = Q.to_ndarray(), R.to_ndarray()
+            res[method] = (np.max(np.abs(q @ r - A)), np.max(np.abs(q.T @ q - np.eye(q.shape[1]))), dt, q, r)
+        dq = np.max(np.abs(res['cgs2'][3] - res['householder'][3]))
+        print(shape, 'qr cgs2 rec %.1e orth %.1e %.1f ms | householder rec %.1e orth %.1e %.1f ms | dQ %.1e' % (
+            res['cgs2'][:3] + res['householder'][:3] + (dq,)))
+        ok = ok and res['householder'][0] < 1e-11 and res['householder'][1] < 1e-12 and dq < 1e-9
     print('ok' if ok else 'FAILED')
     return 0 if ok else 1
 

@@ -176,6 +176,17 @@ class FakeDeviceLib:
             vt[vt_off[i]:vt_off[i] + k * ni] = vv.reshape(-1)
         return np.ones(len(m), dtype=np.int32), nact, np.zeros(len(m), dtype=np.int32)
 
+    def block_qr(self, m, n, a_off, q_off, r_off, A, Q, R):
+        self._count('block_qr')
+        a, q, r = A.numpy(), Q.numpy(), R.numpy()
+        for i in range(len(m)):
+            mi, ni = int(m[i]), int(n[i])
+            k = min(mi, ni)
+            qq, rr = np.linalg.qr(a[a_off[i]:a_off[i] + mi * ni].reshape(mi, ni))
+            sgn = np.where(np.diag(rr) < 0., -1., 1.)
+            q[q_off[i]:q_off[i] + mi * k] = (qq * sgn[None, :]).reshape(-1)
+            r[r_off[i]:r_off[i] + k * ni] = (rr * sgn[:, None]).reshape(-1)
+
     def col_sqnorms(self, rows, cols, ld, X, OUT):
         self._count('col_sqnorms')
         OUT.numpy()[:cols] = np.sum(X.numpy()[:rows * ld].reshape(rows, ld)[:, :cols]**2, axis=0)

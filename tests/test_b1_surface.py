@@ -93,6 +93,19 @@ def test_qr_host_logic(fake_device):
     _check_qr()
 
 
+def test_qr_householder_route_host_logic(fake_device):
+    """np_conserved.qr_method = 'householder' (b200_block_qr_f64: all blocks in one launch) gives the same factors"""
+    from tenpy_b200.linalg import np_conserved as npc
+    old = npc.qr_method
+    npc.qr_method = 'householder'
+    try:
+        n0 = fake_device.calls.get('block_qr', 0)
+        _check_qr()
+        assert fake_device.calls.get('block_qr', 0) > n0
+    finally:
+        npc.qr_method = old
+
+
 @pytest.mark.gpu
 def test_qr_gpu(gpu_lib):
     _check_qr()
