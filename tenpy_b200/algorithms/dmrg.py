@@ -366,6 +366,8 @@ class TwoSiteDMRGEngine:
                                       matvec_order=self.options.get('matvec_order', 'auto'))
         if 'mpo_apply' in self.options:
             self.eff_H.mpo_apply = self.options['mpo_apply']
+        if 'identity_env' in self.options:
+            self.eff_H.identity_env = bool(self.options['identity_env'])
         theta = self.psi.get_theta(self.i0, n=self.n_optimize)
         return self.eff_H.combine_theta(theta)
 

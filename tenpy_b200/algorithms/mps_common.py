@@ -166,6 +166,8 @@ class TwoSiteH:
     # 'tensordot': W0.W1 is applied to LP.theta by npc.tensordot (two block transpositions + a skinny GEMM);
     # 'fused': by the streaming kernel b200_mid_contract_f64 (no charges / one block only).  Opt-in until timed on the GPU.
     mpo_apply = 'tensordot'
+    # skip the identity components of the environments in the split-order matvec (opt-in, see _identity_env_setup)
+    identity_env = False
 
     def __init__(self, env, i0, combine=False, move_right=True, matvec_order='auto'):
         if matvec_order not in ('auto', 'combined', 'split'):
@@ -178,6 +180,7 @@ class TwoSiteH:
         self.W0 = env.H.get_W(i0).replace_labels(['p', 'p*'], ['p0', 'p0*'])
         self.W1 = env.H.get_W(i0 + 1).replace_labels(['p', 'p*'], ['p1', 'p1*'])
         self.dtype = env.H.dtype
+        self._H_mpo = env.H
         self.combine = combine
         self.N = (self.LP.get_leg('vR').ind_len * self.W0.get_leg('p0').ind_len *
                   self.W1.get_leg('p1').ind_len * self.RP.get_leg('vL').ind_len)
@@ -203,6 +206,8 @@ class TwoSiteH:
         if self._W01 is None:
             self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])   # wL p0 p0* p1 p1* wR  (D^2 d^4 numbers)
         th = theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)            # vL p0 p1 vR (read only here)
+        if self.identity_env and self._identity_env_setup():
+            return self._matvec_split_identity(th, labels)
         th = npc.tensordot(self.LP, th, axes=['vR', 'vL'])                   # vR* wR p0 p1 vR      2 D d^2 chi^3
         fused = self._apply_W01_fused(th) if self.mpo_apply == 'fused' else None
         if fused is not None:
@@ -213,6 +218,71 @@ class TwoSiteH:
         th.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
         th = th.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)  # th is ours
         return th.itranspose(labels)
+
+    def _identity_env_setup(self):
+        """In mixed canonical form the component ``wR = IdL`` of `LP` and ``wL = IdR`` of `RP` are identity matrices
+        (``<A|1|A>`` / ``<B|1|B>``; the reference contracts them like every other component).  Checked numerically once
+        per bond (``|LP[IdL] - 1| <= 1e-11 sqrt(chi)``, same for `RP`); if it holds, the matvec skips these components:
+        ``D - 1`` instead of ``D`` large GEMMs on either side.  Prepares `LP` / `RP` without, and ``W0.W1`` with the
+        identity components moved to the end of its MPO legs.  Returns False (and remembers it) if not applicable."""
+        if getattr(self, '_id_env', None) is not None:
+            return self._id_env
+        self._id_env = False
+        H = getattr(self, '_H_mpo', None)
+        if H is None:
+            return False
+        IdL, IdR = H.get_IdL(self.i0), H.get_IdR(self.i0 + 1)
+        if IdL is None or IdR is None or getattr(H, 'explicit_plus_hc', False):
+            return False
+        LP, RP = self.LP, self.RP
+        D_l, D_r = LP.get_leg('wR').ind_len, RP.get_leg('wL').ind_len
+        if D_l < 2 or D_r < 2:
+            return False
+        for part, idx, lab in ((LP, IdL, 'wR'), (RP, IdR, 'wL')):
+            comp = part.take_slice(idx, lab)
+            if np.any(comp.qtotal != 0):
+                return False
+            eye = npc.eye_like(comp, 0, labels=comp.get_leg_labels())
+            dev = npc.norm(comp - eye) if comp.legs[1].qconj == eye.legs[1].qconj else np.inf
+            if not dev <= 1.e-11 * np.sqrt(comp.shape[0]):
+                return False
+        only_l, only_r = np.zeros(D_l, bool), np.zeros(D_r, bool)
+        only_l[IdL], only_r[IdR] = True, True
+
+        def pieces(arr, label, only):            # (all other components, the identity component with a unit leg)
+            rest, one = arr.copy(deep=True), arr.copy(deep=True)
+            rest.iproject(~only, label)
+            one.iproject(only, label)
+            return rest, one
+        self._LP_rest, LP_one = pieces(LP, 'wR', only_l)
+        self._RP_rest, RP_one = pieces(RP, 'wL', only_r)
+        self._leg_IdL = LP_one.get_leg('wR')     # unit legs carrying the charge of the identity component
+        self._leg_IdR = RP_one.get_leg('wL')
+        if self._W01 is None:
+            self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])
+        W_rest, W_one = pieces(self._W01, 'wL', only_l)
+        W01p = npc.concatenate([W_rest, W_one], axis='wL')                   # wL: [others ..., IdL]
+        W_rest, W_one = pieces(W01p, 'wR', only_r)
+        self._W01p = npc.concatenate([W_rest, W_one], axis='wR')             # wR: [others ..., IdR]
+        self._mask_rest_r = np.arange(D_r) < D_r - 1
+        self._id_env = True
+        return True
+
+    def _matvec_split_identity(self, th, labels):
+        """Split-order matvec without the identity components of the environments: ``T1 = [LP_rest . theta, theta]``,
+        ``T2 = (W0 W1) . T1``, ``result = T2[rest] . RP_rest + T2[IdR]``."""
+        t1 = npc.tensordot(self._LP_rest, th, axes=['vR', 'vL'])             # vR* wR' p0 p1 vR   2 (D-1) d^2 chi^3
+        th_id = th.add_leg(self._leg_IdL, 0, axis=1, label='wR').ireplace_label('vL', 'vR*')
+        t1 = npc.concatenate([t1, th_id], axis='wR')                         # wR: [others ..., IdL]
+        t2 = npc.tensordot(t1, self._W01p, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])   # vR* vR p0 p1 wR
+        direct = t2.take_slice(len(self._mask_rest_r) - 1, 'wR')            # component IdR: no contraction with RP
+        t2.iproject(self._mask_rest_r, 'wR')
+        out = npc.tensordot(t2, self._RP_rest, axes=[['vR', 'wR'], ['vL', 'wL']])   # vR* p0 p1 vL*  2 (D-1) d^2 chi^3
+        out.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
+        direct.ireplace_label('vR*', 'vL').itranspose(out.get_leg_labels())
+        out.iadd_prefactor_other(1., direct)
+        out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
+        return out.itranspose(labels)
 
     def _apply_W01_fused(self, th):
         """``W0.W1`` applied to ``th[vR*, wR, p0, p1, vR]`` in one streaming pass that keeps the layout: the result

@@ -4,7 +4,8 @@ on the benchmark workload (short chain), with energies compared against the defa
     python tests/dev_optins_gpu_check.py [chi=1024] [L=24]
 
 configurations: default | mpo_apply='fused' (b200_mid_contract_f64) | + lanczos device_scalars
-(b200_lanczos_update_dev_f64 / b200_scal_rsqrt_dev_f64) | + jacobi_eig_kernel_v2 (b200_svd_set_eig_variant(2)).
+(b200_lanczos_update_dev_f64 / b200_scal_rsqrt_dev_f64) | + jacobi_eig_kernel_v2 (b200_svd_set_eig_variant(2)) |
+identity_env (skip the identity components LP[IdL], RP[IdR]: D-1 instead of D large GEMMs per side; host logic only).
 Prints one JSON line per configuration: seconds per sweep (CUDA events, 2nd of two sweeps), E, kernel family times.
 """
 import json
@@ -30,13 +31,17 @@ def main():
     configs = [('default', {}, 1),
                ('fused_mpo_apply', {'mpo_apply': 'fused'}, 1),
                ('fused+device_scalars', {'mpo_apply': 'fused', 'device_scalars': True}, 1),
-               ('fused+device_scalars+eig_v2', {'mpo_apply': 'fused', 'device_scalars': True}, 2)]
+               ('fused+device_scalars+eig_v2', {'mpo_apply': 'fused', 'device_scalars': True}, 2),
+               ('identity_env', {'identity_env': True}, 1),
+               ('identity_env+device_scalars+eig_v2', {'identity_env': True, 'device_scalars': True}, 2)]
     E_ref = None
     for name, extra, eig_variant in configs:
         opts = dict(base)
         opts['lanczos_params'] = {'N_min': 10, 'N_max': 10, 'device_scalars': bool(extra.get('device_scalars', False))}
         if 'mpo_apply' in extra:
             opts['mpo_apply'] = extra['mpo_apply']
+        if 'identity_env' in extra:
+            opts['identity_env'] = True
         psi = bench.synthetic_mps(model, L, chi, 2, seed=0)
         eng = dmrg.TwoSiteDMRGEngine(psi, model, opts)
         old = lib.svd_set_eig_variant(eig_variant)

@@ -417,3 +417,59 @@ def test_split_matvec_shares_buffers_without_charges(fake_device):
     theta = H.combine_theta(psi.get_theta(3, 2))
     if theta.stored_blocks > 1:
         assert theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)._buf.data_ptr() != theta._buf.data_ptr()
+
+
+def test_matvec_identity_env(fake_device):
+    """split-order matvec with `identity_env=True`: the identity components LP[IdL], RP[IdR] of the environments are
+    skipped (D-1 instead of D large GEMMs per side); same result on canonical states (dense, U(1), U(1)xU(1)); falls back
+    when the environment component is not the identity"""
+    from tenpy_b200.models import TFIChain, SpinChain, FermiHubbardChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg import np_conserved as npc
+    cases = [(TFIChain({'L': 8, 'J': 1., 'g': 1.1, 'conserve': None}), ['up'] * 8, None),
+             (SpinChain({'L': 8, 'Jx': 1., 'Jy': 1., 'Jz': 0.7, 'conserve': 'Sz'}), ['up', 'down'] * 4, True),
+             (FermiHubbardChain({'L': 6, 't': 1., 'U': 4., 'mu': 0.}), ['up', 'down'] * 3, True)]
+    for M, state, mixer in cases:
+        psi = MPS.from_product_state(M.lat_sites, state)
+        eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': mixer, 'combine': True, 'matvec_order': 'combined',
+                                              'trunc_params': {'chi_max': 24, 'svd_min': 1e-12}})
+        eng.sweep()
+        eng.sweep()
+        eng.mixer_cleanup()
+        psi.canonical_form()
+        eng.env.clear()
+        used = 0
+        for i0 in range(psi.L - 1):
+            Hc = TwoSiteH(eng.env, i0, combine=True, matvec_order='combined')
+            Hi = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+            Hi.identity_env = True
+            theta = Hc.combine_theta(psi.get_theta(i0, 2))
+            a, b = Hc.matvec(theta), Hi.matvec(theta)
+            used += int(bool(Hi._id_env))
+            assert a.get_leg_labels() == b.get_leg_labels()
+            assert npc.norm(a - b) <= 1e-11 * max(npc.norm(a), 1e-300), (i0, npc.norm(a - b), npc.norm(a))
+        assert used >= psi.L - 3            # the boundary bonds may have 1-dimensional MPO legs
+    # not applicable: an environment whose IdL component is not the identity -> the plain split order, same result
+    H = TwoSiteH(eng.env, 2, combine=True, matvec_order='split')
+    H.identity_env = True
+    H.LP = H.LP * 1.5
+    Href = TwoSiteH(eng.env, 2, combine=True, matvec_order='split')
+    Href.LP = Href.LP * 1.5
+    theta = H.combine_theta(psi.get_theta(2, 2))
+    assert npc.norm(H.matvec(theta) - Href.matvec(theta)) < 1e-13 * npc.norm(Href.matvec(theta)) and H._id_env is False
+    # whole runs with the option
+    g = h.load('dmrg.npz')
+    M = TFIChain({'L': 20, 'J': 1., 'g': 1., 'conserve': None})
+    res, psi = _run_dmrg(M, ['up'] * 20, {'mixer': None, 'max_E_err': 1e-10, 'combine': True, 'matvec_order': 'split',
+                                         'identity_env': True, 'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
+    assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
+    assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
+    L = 16
+    M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 1., 'conserve': 'Sz'})
+    opts = {'mixer': True, 'mixer_params': {'amplitude': 1e-5, 'decay': 2., 'disable_after': 6}, 'max_E_err': 1e-11,
+            'max_S_err': 1e-8, 'trunc_params': {'chi_max': 60, 'svd_min': 1e-10}, 'combine': True, 'max_sweeps': 20,
+            'matvec_order': 'split', 'identity_env': True}
+    res, psi = _run_dmrg(M, ['up', 'down'] * (L // 2), opts)
+    assert abs(res['E'] - g['xxz_E']) < 1e-10 * abs(g['xxz_E'])
