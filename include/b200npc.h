@@ -172,6 +172,12 @@ int b200_block_qr_f64(int64_t nblocks, const int64_t *m_host, const int64_t *n_h
  * matvec (TwoSiteH.matvec, reference mps_common.py:1341-1343) into one streaming pass.  Opt-in (round 2: GPU timing). */
 int b200_mid_contract_f64(int64_t K, int64_t N, int64_t outer, int64_t inner, const double *M_dev, const double *T,
                           double *OUT, b200_stream_t stream);
+/* two-segment version: [OUT1; OUT2][o, n, i] = sum_k M[n, k] [T1; T2][o, k, i] with K = K1 + K2 rows taken from T1 then
+ * T2 and N = N1 + N2 rows written to OUT1 then OUT2 (M: N x K).  The matvec without the identity components of the
+ * environments in one pass: T1 = LP_rest.theta, T2 = theta, OUT1 -> contraction with RP_rest, OUT2 -> added to the result. */
+int b200_mid_contract2_f64(int64_t K1, int64_t K2, int64_t N1, int64_t N2, int64_t outer, int64_t inner,
+                           const double *M_dev, const double *T1, const double *T2, double *OUT1, double *OUT2,
+                           b200_stream_t stream);
 
 /* OUT[c] = sum_r X[r*ld + c]^2 for a row-major (rows x cols) matrix (leverage scores of the null-space
  * completion in np_conserved.svd; no reference counterpart: LAPACK returns a complete basis by itself) */

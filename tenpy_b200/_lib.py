@@ -63,6 +63,7 @@ _SIGNATURES = {
     'b200_col_sqnorms_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     'b200_block_qr_worksize': (c_i64, [c_i64, c_i64p, c_i64p]),
     'b200_block_qr_f64': (ctypes.c_int, [c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'b200_mid_contract2_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200_mid_contract_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'b200_svd_set_deflation': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_eig_variant': (ctypes.c_int, [ctypes.c_int]),
@@ -308,6 +309,13 @@ class DeviceLib:
         with _Prof(self, 'move'):
             self._check(self.c.b200_mid_contract_f64(int(K), int(N), int(outer), int(inner), _ptr(M), _ptr(T),
                                                      _ptr(OUT), self.stream()))
+
+    def mid_contract2(self, K1, K2, N1, N2, outer, inner, M, T1, T2, OUT1, OUT2):
+        """[OUT1; OUT2][o, n, i] = sum_k M[n, k] [T1; T2][o, k, i] (include/b200npc.h)"""
+        with _Prof(self, 'move'):
+            self._check(self.c.b200_mid_contract2_f64(int(K1), int(K2), int(N1), int(N2), int(outer), int(inner),
+                                                      _ptr(M), _ptr(T1), _ptr(T2), _ptr(OUT1), _ptr(OUT2),
+                                                      self.stream()))
 
     # -- decompositions
     def block_svd(self, m, n, a_off, u_off, s_off, vt_off, A, U, S, VT):

@@ -272,6 +272,15 @@ class TwoSiteH:
         """Split-order matvec without the identity components of the environments: ``T1 = [LP_rest . theta, theta]``,
         ``T2 = (W0 W1) . T1``, ``result = T2[rest] . RP_rest + T2[IdR]``."""
         t1 = npc.tensordot(self._LP_rest, th, axes=['vR', 'vL'])             # vR* wR' p0 p1 vR   2 (D-1) d^2 chi^3
+        if self.mpo_apply == 'fused':
+            fused = self._apply_W01_fused_identity(t1, th)
+            if fused is not None:
+                y_rest, y_id = fused                                         # vR* p0 p1 wR' vR ; vR* p0 p1 vR
+                out = npc.tensordot(y_rest, self._RP_rest_t, axes=[['wR', 'vR'], ['wL', 'vL']])
+                out.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
+                out.iadd_prefactor_other(1., y_id.ireplace_label('vR*', 'vL'))
+                out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
+                return out.itranspose(labels)
         th_id = th.add_leg(self._leg_IdL, 0, axis=1, label='wR').ireplace_label('vL', 'vR*')
         t1 = npc.concatenate([t1, th_id], axis='wR')                         # wR: [others ..., IdL]
         t2 = npc.tensordot(t1, self._W01p, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])   # vR* vR p0 p1 wR
@@ -283,6 +292,48 @@ class TwoSiteH:
         out.iadd_prefactor_other(1., direct)
         out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
         return out.itranspose(labels)
+
+    def _apply_W01_fused_identity(self, t1, th):
+        """``[Y_rest; Y_IdR] = (W0 W1) . [T1_rest; theta]`` in one streaming pass (b200_mid_contract2_f64): both inputs
+        are read once, both outputs come out in the layout their consumer wants.  Dense (one block) only; None if not
+        applicable."""
+        from .. import backend
+        if t1._layout.nblocks != 1 or th._layout.nblocks != 1 or self._W01._layout.nblocks != 1 or \
+                t1.get_leg_labels() != ['vR*', 'wR', 'p0', 'p1', 'vR'] or th.get_leg_labels() != ['vL', 'p0', 'p1', 'vR']:
+            return None
+        chi_l, Dm1, d0, d1, chi_r = t1.shape
+        K1, K2 = Dm1 * d0 * d1, d0 * d1
+        if K1 + K2 > 32:
+            return None
+        if getattr(self, '_M_id', None) is None:
+            # (W0 W1) as a matrix [(p0' p1' wR), (wL p0 p1)] with the identity components moved to the end of both
+            # index groups; D^2 d^4 model constants, permuted on the host once per bond
+            H = self._H_mpo
+            IdL, IdR = H.get_IdL(self.i0), H.get_IdR(self.i0 + 1)
+            W = self._W01.transpose(['p0', 'p1', 'wR', 'wL', 'p0*', 'p1*']).to_ndarray()
+            D_r, D_l = W.shape[2], W.shape[3]
+            rest_r = [x for x in range(D_r) if x != IdR]
+            rest_l = [x for x in range(D_l) if x != IdL]
+            rows = np.concatenate([W[:, :, rest_r].reshape(d0 * d1 * len(rest_r), D_l, d0, d1),
+                                   W[:, :, IdR].reshape(d0 * d1, D_l, d0, d1)], axis=0)
+            M = np.concatenate([rows[:, rest_l].reshape(rows.shape[0], -1), rows[:, IdL].reshape(rows.shape[0], -1)],
+                               axis=1)
+            self._M_id = backend.to_device(np.ascontiguousarray(M))
+            self._RP_rest_t = self._RP_rest.transpose(['wL', 'vL', 'vL*'])
+            self._N1 = d0 * d1 * len(rest_r)
+            self._fused_legs = (self._W01.get_leg('p0'), self._W01.get_leg('p1'), self._RP_rest.get_leg('wL').conj())
+        N1, N2 = self._N1, K2
+        p0leg, p1leg, wleg = self._fused_legs
+        legs_r = [t1.legs[0], p0leg, p1leg, wleg, t1.legs[4]]
+        legs_i = [t1.legs[0], p0leg, p1leg, t1.legs[4]]
+        y_r = npc.Array(legs_r, np.float64, None, ['vR*', 'p0', 'p1', 'wR', 'vR'])
+        y_i = npc.Array(legs_i, np.float64, None, ['vR*', 'p0', 'p1', 'vR'])
+        lay_r, _ = npc.BlockLayout.from_legs(legs_r, np.zeros((1, 5), np.int64))
+        lay_i, _ = npc.BlockLayout.from_legs(legs_i, np.zeros((1, 4), np.int64))
+        buf_r = backend.zeros(lay_r.size) if lay_r.has_padding else backend.empty(lay_r.size)
+        buf_i = backend.zeros(lay_i.size) if lay_i.has_padding else backend.empty(lay_i.size)
+        backend.get_lib().mid_contract2(K1, K2, N1, N2, chi_l, chi_r, self._M_id, t1._buf, th._buf, buf_r, buf_i)
+        return y_r._set_blocks(lay_r, buf_r), y_i._set_blocks(lay_i, buf_i)
 
     def _apply_W01_fused(self, th):
         """``W0.W1`` applied to ``th[vR*, wR, p0, p1, vR]`` in one streaming pass that keeps the layout: the result

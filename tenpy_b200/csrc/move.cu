@@ -116,9 +116,43 @@ __global__ void __launch_bounds__(MV_THREADS) mid_contract_kernel(int K, int N, 
     for (int64_t o = blockIdx.y; o < outer; o += gridDim.y) midc::column<KMAX>(o, i, K, N, inner, sM, T, OUT);
 }
 
+template <int KMAX>
+__global__ void __launch_bounds__(MV_THREADS) mid_contract2_kernel(int K1, int K2, int N1, int N2, int64_t outer,
+                                                                   int64_t inner, const double *__restrict__ M,
+                                                                   const double *__restrict__ T1,
+                                                                   const double *__restrict__ T2,
+                                                                   double *__restrict__ OUT1, double *__restrict__ OUT2) {
+    extern __shared__ double sM[];
+    for (int idx = threadIdx.x; idx < (N1 + N2) * (K1 + K2); idx += blockDim.x) sM[idx] = M[idx];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= inner) return;
+    for (int64_t o = blockIdx.y; o < outer; o += gridDim.y)
+        midc::column2<KMAX>(o, i, K1, K2, N1, N2, inner, sM, T1, T2, OUT1, OUT2);
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_mid_contract2_f64(int64_t K1, int64_t K2, int64_t N1, int64_t N2, int64_t outer, int64_t inner,
+                                      const double *M_dev, const double *T1, const double *T2, double *OUT1, double *OUT2,
+                                      b200_stream_t stream) {
+    const int64_t K = K1 + K2, N = N1 + N2;
+    if (outer <= 0 || inner <= 0 || N <= 0) return B200_OK;
+    if (K1 < 0 || K2 < 0 || N1 < 0 || N2 < 0 || K <= 0 || K > 32 || N > 1024)
+        return set_error(B200_ERR_ARG, "mid_contract2: K=%lld (1..32), N=%lld (<=1024)", (long long)K, (long long)N);
+    const unsigned gx = (unsigned)((inner + MV_THREADS - 1) / MV_THREADS);
+    const unsigned gy = (unsigned)(outer < 65535 ? outer : 65535);
+    const size_t smem = (size_t)(N * K) * sizeof(double);
+    if (smem > 48 * 1024) return set_error(B200_ERR_ARG, "mid_contract2: matrix %lld x %lld too large", (long long)N, (long long)K);
+    if (K <= 16)
+        mid_contract2_kernel<16><<<dim3(gx, gy), MV_THREADS, smem, (cudaStream_t)stream>>>((int)K1, (int)K2, (int)N1, (int)N2, outer, inner, M_dev, T1, T2, OUT1, OUT2);
+    else
+        mid_contract2_kernel<32><<<dim3(gx, gy), MV_THREADS, smem, (cudaStream_t)stream>>>((int)K1, (int)K2, (int)N1, (int)N2, outer, inner, M_dev, T1, T2, OUT1, OUT2);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
 
 extern "C" int b200_mid_contract_f64(int64_t K, int64_t N, int64_t outer, int64_t inner, const double *M_dev,
                                      const double *T, double *OUT, b200_stream_t stream) {

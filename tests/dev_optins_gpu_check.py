@@ -33,7 +33,9 @@ def main():
                ('fused+device_scalars', {'mpo_apply': 'fused', 'device_scalars': True}, 1),
                ('fused+device_scalars+eig_v2', {'mpo_apply': 'fused', 'device_scalars': True}, 2),
                ('identity_env', {'identity_env': True}, 1),
-               ('identity_env+device_scalars+eig_v2', {'identity_env': True, 'device_scalars': True}, 2)]
+               ('identity_env+fused', {'identity_env': True, 'mpo_apply': 'fused'}, 1),
+               ('identity_env+fused+device_scalars+eig_v2', {'identity_env': True, 'mpo_apply': 'fused',
+                                                             'device_scalars': True}, 2)]
     E_ref = None
     for name, extra, eig_variant in configs:
         opts = dict(base)

@@ -144,6 +144,20 @@ class FakeDeviceLib:
         t = T.numpy()[:outer * K * inner].reshape(outer, K, inner)
         OUT.numpy()[:outer * N * inner] = np.einsum('nk,oki->oni', m, t).reshape(-1)
 
+    def mid_contract2(self, K1, K2, N1, N2, outer, inner, M, T1, T2, OUT1, OUT2):
+        self._count('mid_contract2')
+        m = M.numpy()[:(N1 + N2) * (K1 + K2)].reshape(N1 + N2, K1 + K2)
+        parts = []
+        if K1:
+            parts.append(T1.numpy()[:outer * K1 * inner].reshape(outer, K1, inner))
+        if K2:
+            parts.append(T2.numpy()[:outer * K2 * inner].reshape(outer, K2, inner))
+        res = np.einsum('nk,oki->oni', m, np.concatenate(parts, axis=1))
+        if N1:
+            OUT1.numpy()[:outer * N1 * inner] = res[:, :N1].reshape(-1)
+        if N2:
+            OUT2.numpy()[:outer * N2 * inner] = res[:, N1:].reshape(-1)
+
     deflation = True
     deflation_tol = 0.
 

@@ -451,6 +451,23 @@ def test_matvec_identity_env(fake_device):
             assert a.get_leg_labels() == b.get_leg_labels()
             assert npc.norm(a - b) <= 1e-11 * max(npc.norm(a), 1e-300), (i0, npc.norm(a - b), npc.norm(a))
         assert used >= psi.L - 3            # the boundary bonds may have 1-dimensional MPO legs
+    # dense case with the fused two-segment kernel (b200_mid_contract2_f64)
+    M0, state0, _ = cases[0]
+    psi0 = MPS.from_product_state(M0.lat_sites, state0)
+    eng0 = dmrg.TwoSiteDMRGEngine(psi0, M0, {'mixer': None, 'combine': True, 'trunc_params': {'chi_max': 24, 'svd_min': 1e-12}})
+    eng0.sweep()
+    eng0.sweep()
+    psi0.canonical_form()
+    eng0.env.clear()
+    for i0 in range(1, psi0.L - 2):
+        Hc = TwoSiteH(eng0.env, i0, combine=True, matvec_order='combined')
+        Hf = TwoSiteH(eng0.env, i0, combine=True, matvec_order='split')
+        Hf.identity_env, Hf.mpo_apply = True, 'fused'
+        theta = Hc.combine_theta(psi0.get_theta(i0, 2))
+        n0 = fake_device.calls.get('mid_contract2', 0)
+        a, b = Hc.matvec(theta), Hf.matvec(theta)
+        assert fake_device.calls.get('mid_contract2', 0) == n0 + 1
+        assert npc.norm(a - b) <= 1e-11 * max(npc.norm(a), 1e-300)
     # not applicable: an environment whose IdL component is not the identity -> the plain split order, same result
     H = TwoSiteH(eng.env, 2, combine=True, matvec_order='split')
     H.identity_env = True
