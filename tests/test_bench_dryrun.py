@@ -1,0 +1,40 @@
+"""bench.py's GPU arm executed on the numpy test double with stubbed CUDA timing (tests/dev_bench_dryrun.py): guards the
+host side of the benchmark script -- JSON contract keys, probes, N=1 path -- on a box without a GPU.  The numbers of a
+dry run mean nothing and are not checked."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_contract_keys_dry_run():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'dev_bench_dryrun.py'), '--L', '12', '--chi', '16',
+                          '--steps', '1', '--warmup', '1', '--cpu-bonds', '1'], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+        assert key in d, key
+    assert d['higher_is_better'] is False and d['dtype'] == 'f64' and 'workload' in d['config']
+    for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert key in d['roofline'], key
+    for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
+        assert key in d['e2e'], key
+    for key in ('value', 'unit', 'cores', 'kind', 'sample'):
+        assert key in d['cpu_baseline'], key
+    assert 'error' not in d['matvec_orders'] and 'error' not in d['roofline_svd']['workload_theta']
+    assert all('error' not in p for p in d['blocksparse_matvec'])
+
+
+def test_bench_reference_arm():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--L', '16', '--chi', '32',
+                          '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d['impl'] == 'reference' and d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
+    assert d['value'] > 0 and d['config']['chi'] == 32
