@@ -20,6 +20,8 @@ logger = logging.getLogger(__name__)
 
 __all__ = ['KrylovBased', 'LanczosGroundState', 'lanczos']
 
+DEVICE_SCALARS_DEFAULT = False   # default of the Lanczos option `device_scalars` (see tenpy_b200/optins.py)
+
 
 class KrylovBased:
     """Base class: option parsing, cache and result assembly (reference krylov_based.py:30)."""
@@ -81,7 +83,7 @@ class LanczosGroundState(KrylovBased):
         if self.N_cache < 2:
             raise ValueError('Need to cache at least two vectors.')
         # extension (opt-in): keep (alpha, beta) on the device and read them back in chunks, see _build_krylov_device
-        self.device_scalars = bool(self.options.get('device_scalars', False))
+        self.device_scalars = bool(self.options.get('device_scalars', DEVICE_SCALARS_DEFAULT))
         self.sync_every = max(1, int(self.options.get('sync_every', 2)))
 
     def run(self):
