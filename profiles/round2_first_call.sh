@@ -20,3 +20,6 @@ for tag in ('default', 'optins'):
     except Exception as e:
         print(tag, 'no result:', e)
 PY
+# configs[2] / [3] end to end (block-sparse DMRG at the target bond dimensions); separate call if the budget is tight
+# timeout 600 python profiles/blocksparse_dmrg_probe.py xxz --L 100 --chi 1024 --ramp 6 --timed 2 > $T/r02a_xxz.json 2> $T/r02a_xxz.err
+# timeout 900 python profiles/blocksparse_dmrg_probe.py hubbard --L 64 --chi 2048 --ramp 7 --timed 2 > $T/r02a_hubbard.json 2> $T/r02a_hubbard.err
