@@ -202,6 +202,9 @@ int b200_svd_set_deflation(int on);
 /* pivot eigen-solver of the Jacobi rounds: 1 = jacobi_eig_kernel (default), 2 = jacobi_eig_kernel_v2 (two barriers per
  * rotation set, csrc/jacobi_eig_core.cuh; host-verified, to be timed on the GPU in round 2); returns the old value */
 int b200_svd_set_eig_variant(int variant);
+/* inner sweeps of the version-2 pivot eigen-solver (1..16, default 4): profiles/jacobi_sweeps_study.md finds the number
+ * of outer sweeps unchanged between 2 and 4; returns the old value */
+int b200_svd_set_eig_inner_sweeps(int n);
 /* additional deflation threshold relative to |A_i|_F (default 0 = rounding level only): directions with a
  * singular value below tol_rel*|A_i|_F are treated like the negligible ones; returns the old value.  A DMRG
  * truncation discards them anyway (the reference's `svd_min`, truncation.py:196). */

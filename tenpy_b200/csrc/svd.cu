@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(JTHREADS)
 __global__ void __launch_bounds__(JTHREADS)
     jacobi_eig_kernel_v2(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
                          const int *__restrict__ done, double tol_scale, const double *__restrict__ Gbuf, int nsplit,
-                         double *__restrict__ QTbuf, int *__restrict__ flags) {
+                         double *__restrict__ QTbuf, int *__restrict__ flags, int inner_sweeps) {
     static_assert(jeig::N == JP && jeig::LD == JLDG, "pivot order / smem stride of jacobi_eig_core.cuh");
     __shared__ double sGa[JP * JLDG], sGb[JP * JLDG];
     __shared__ double sQa[JP * JLDG], sQb[JP * JLDG];
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(JTHREADS)
     __syncthreads();
     double *Gc = sGa, *Gn = sGb, *Qc = sQa, *Qn = sQb;
     const double tol_in = 1e-15;
-    for (int sweep = 0; sweep < J_INNER_SWEEPS; ++sweep) {
+    for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
         int any = 0;
         for (int step = 0; step < JP - 1; ++step) {
             if (tid < jeig::NPAIR) any |= jeig::phase_params(tid, step, Gc, defl2, tol_in, s_partner, s_alpha, s_beta);
@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(128)
 
 // ---- host driver -----------------------------------------------------------------------------------
 static int g_eig_variant = 1;   // pivot eigen-solver: 1 = jacobi_eig_kernel (GPU-verified), 2 = jacobi_eig_kernel_v2
+static int g_eig_inner_sweeps = J_INNER_SWEEPS;   // inner sweeps of version 2 (version 1: fixed J_INNER_SWEEPS)
 struct JLayout {
     std::vector<JMat> mats;
     std::vector<int> cta_mat;
@@ -750,7 +751,7 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
             B200_CHECK_LAUNCH();
             if (g_eig_variant == 2)
                 jacobi_eig_kernel_v2<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit,
-                                                               d_QT, d_flags);
+                                                               d_QT, d_flags, g_eig_inner_sweeps);
             else
                 jacobi_eig_kernel<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit, d_QT,
                                                             d_flags);
@@ -865,6 +866,12 @@ extern "C" double b200_svd_set_deflation_tol(double tol_rel) {
 extern "C" int b200_svd_set_eig_variant(int variant) {
     int old = g_eig_variant;
     if (variant == 1 || variant == 2) g_eig_variant = variant;
+    return old;
+}
+
+extern "C" int b200_svd_set_eig_inner_sweeps(int n) {
+    int old = g_eig_inner_sweeps;
+    if (n >= 1 && n <= 16) g_eig_inner_sweeps = n;
     return old;
 }
 

@@ -37,18 +37,22 @@ def main():
         ok = ok and res[2][0] < 1e-11 and res[2][1] < 1e-11 and res[2][2] < 1e-11
     n = 2048
     th = npc.Array.from_ndarray_trivial(rng.standard_normal((n, n)))
-    for variant in (1, 2):
+    for variant, inner in ((1, 4), (2, 4), (2, 3), (2, 2), (2, 1)):
         old = lib.svd_set_eig_variant(variant)
+        old_in = lib.svd_set_eig_inner_sweeps(inner)
         try:
             npc.svd(th)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            npc.svd(th)
+            U, S, VH = npc.svd(th)
             torch.cuda.synchronize()
-            print('2048x2048 generic, eig variant %d: %.1f ms, %d sweeps' % (variant, (time.perf_counter() - t0) * 1e3,
-                                                                            npc.svd_stats['jacobi_sweeps'][-1]))
+            dt = (time.perf_counter() - t0) * 1e3
+            rec = float(npc.norm(npc.tensordot(U.scale_axis(S, 1), VH, axes=1) - th) / npc.norm(th))
+            print('2048x2048 generic, eig variant %d, %d inner sweeps: %.1f ms, %d outer sweeps, rec.err %.1e' % (
+                variant, inner, dt, npc.svd_stats['jacobi_sweeps'][-1], rec))
         finally:
             lib.svd_set_eig_variant(old)
+            lib.svd_set_eig_inner_sweeps(old_in)
     # Householder block QR (b200_block_qr_f64) against the Gram-Schmidt route and numpy
     for shape in [(7, 4), (4, 7), (64, 64), (300, 130), (512, 512)]:
         A = rng.standard_normal(shape)
