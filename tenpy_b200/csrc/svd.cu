@@ -35,7 +35,8 @@ constexpr int JTHREADS = 256;
 constexpr int JLDG = JP + 1;
 constexpr int JLDQT = JP + 4;
 constexpr int J_NSPLIT_MAX = 16;    // column splits of the streaming phases of one pair
-constexpr int J_INNER_SWEEPS = 4;   // the pivot block only has to be diagonalised "well enough" per round
+constexpr int J_INNER_SWEEPS = 2;   // the pivot block only has to be diagonalised "well enough" per round: the outer sweep
+                                    // count is the same for 2 and 4 (profiles/jacobi_sweeps_study.md; 4 until round 1)
 
 struct JMat {
     int64_t y_off, w_off, snorm_off;       // element offsets into the f64 work area
