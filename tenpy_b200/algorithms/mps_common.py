@@ -45,6 +45,21 @@ _TWO_SITE_CHAINS = {
 }
 
 
+_EYE_CACHE = {}
+
+
+def _cached_eye(comp):
+    """identity Array with the legs of the square 2D Array `comp`, kept on the device per leg structure (all saturated
+    bonds of a chain share one); avoids building and uploading a dense identity for every bond"""
+    key = (comp.legs[0].content_key(), tuple(comp.get_leg_labels()))
+    eye = _EYE_CACHE.get(key)
+    if eye is None or eye._buf is None or eye._buf.device != comp._buf.device:
+        if len(_EYE_CACHE) > 64:
+            _EYE_CACHE.clear()
+        eye = _EYE_CACHE[key] = npc.eye_like(comp, 0, labels=comp.get_leg_labels())
+    return eye
+
+
 class OneSiteH:
     r"""Effective Hamiltonian ``LP--W0--RP`` acting on the one-site wave function (reference mps_common.py:1040).
 
@@ -242,7 +257,7 @@ class TwoSiteH:
             comp = part.take_slice(idx, lab)
             if np.any(comp.qtotal != 0):
                 return False
-            eye = npc.eye_like(comp, 0, labels=comp.get_leg_labels())
+            eye = _cached_eye(comp)
             dev = npc.norm(comp - eye) if comp.legs[1].qconj == eye.legs[1].qconj else np.inf
             if not dev <= 1.e-11 * np.sqrt(comp.shape[0]):
                 return False

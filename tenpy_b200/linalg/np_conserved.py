@@ -607,14 +607,25 @@ class Array:
             if m.shape != (self.shape[ax],):
                 raise ValueError('mask has wrong length')
             leg = self.legs[ax]
-            map_qind, block_masks, new_leg = leg.project(m)
+            lay = self._layout
+            key = ('J', ax, leg.content_key(), m.tobytes())
+            cached = lay.cache.get(key)
+            if cached is None:
+                map_qind, block_masks, new_leg = leg.project(m)
+                new_legs_ = list(self.legs)
+                new_legs_[ax] = new_leg
+                new_layout, rec, pool = plan_project(lay, self.legs, ax, map_qind, block_masks, new_leg, new_legs_)
+                cached = (map_qind, block_masks, new_leg, new_layout, rec,
+                          backend.to_device(rec) if new_layout.nblocks else None,
+                          backend.to_device(pool) if new_layout.nblocks else None)
+                if len(lay.cache) < 256:
+                    lay.cache[key] = cached
+            map_qind, block_masks, new_leg, new_layout, rec, rec_dev, pool_dev = cached
             new_legs = list(self.legs)
             new_legs[ax] = new_leg
-            lay = self._layout
-            new_layout, rec, pool = plan_project(lay, self.legs, ax, map_qind, block_masks, new_leg, new_legs)
             if new_layout.nblocks:
                 buf = backend.zeros(new_layout.size)
-                backend.get_lib().take_blocks(rec, backend.to_device(rec), backend.to_device(pool), self._buf, buf)
+                backend.get_lib().take_blocks(rec, rec_dev, pool_dev, self._buf, buf)
             else:
                 buf = None
             self.legs = new_legs
@@ -855,10 +866,17 @@ class Array:
         lay = self._layout
         if lay.nblocks == 0:
             return res
-        new_layout, rec = plan_take_slice(lay, axes, pos[:, 0], pos[:, 1])
+        key = ('TS', tuple(axes), pos.tobytes())
+        cached = lay.cache.get(key)
+        if cached is None:
+            new_layout, rec = plan_take_slice(lay, axes, pos[:, 0], pos[:, 1])
+            cached = (new_layout, rec, backend.to_device(rec) if new_layout.nblocks else None)
+            if len(lay.cache) < 256:
+                lay.cache[key] = cached
+        new_layout, rec, rec_dev = cached
         if new_layout.nblocks:
             buf = _dest_buffer(new_layout, rec)
-            backend.get_lib().copy_blocks(rec, backend.to_device(rec), self._buf, buf)
+            backend.get_lib().copy_blocks(rec, rec_dev, self._buf, buf)
             res._set_blocks(new_layout, buf)
         return res
 
@@ -879,9 +897,18 @@ class Array:
         lay = self._layout
         if lay.nblocks == 0:
             return res
-        new_layout, rec = plan_add_leg(lay, axis, qi, ri, leg.get_block_sizes()[qi])
-        buf = backend.zeros(new_layout.size)
-        backend.get_lib().copy_blocks(rec, backend.to_device(rec), self._buf, buf)
+        bs = int(leg.get_block_sizes()[qi])
+        key = ('AL', axis, int(qi), int(ri), bs)
+        cached = lay.cache.get(key)
+        if cached is None:
+            new_layout, rec = plan_add_leg(lay, axis, qi, ri, bs)
+            cached = (new_layout, rec, backend.to_device(rec))
+            if len(lay.cache) < 256:
+                lay.cache[key] = cached
+        new_layout, rec, rec_dev = cached
+        # a unit block needs no zero fill: the copy covers it
+        buf = _dest_buffer(new_layout, rec) if bs == 1 else backend.zeros(new_layout.size)
+        backend.get_lib().copy_blocks(rec, rec_dev, self._buf, buf)
         return res._set_blocks(new_layout, buf)
 
     def extend(self, axis, extra):
@@ -988,14 +1015,21 @@ def concatenate(arrays, axis=0, copy=True):
     legs[axis] = new_leg
     res = Array(legs, np.float64, first.qtotal)
     res._labels = list(first._labels)
-    new_layout, recs = plan_concatenate([a._layout for a in arrays], legs, axis, shifts)
+    key = ('CAT', axis, tuple(a._layout.uid for a in arrays[1:]), tuple(l.content_key() for l in legs))
+    cached = first._layout.cache.get(key)
+    if cached is None or any(c is not a._layout for c, a in zip(cached[3], arrays)):
+        new_layout, recs = plan_concatenate([a._layout for a in arrays], legs, axis, shifts)
+        cached = (new_layout, recs, [backend.to_device(r) if len(r) else None for r in recs], [a._layout for a in arrays])
+        if len(first._layout.cache) < 256:
+            first._layout.cache[key] = cached
+    new_layout, recs, recs_dev = cached[:3]
     if new_layout.nblocks == 0:
         return res
     buf = backend.zeros(new_layout.size) if new_layout.has_padding else backend.empty(new_layout.size)
     lib = backend.get_lib()
-    for a, rec in zip(arrays, recs):
+    for a, rec, rec_dev in zip(arrays, recs, recs_dev):
         if len(rec):
-            lib.copy_blocks(rec, backend.to_device(rec), a._buf, buf)
+            lib.copy_blocks(rec, rec_dev, a._buf, buf)
     return res._set_blocks(new_layout, buf)
 
 
