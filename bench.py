@@ -215,7 +215,9 @@ def workload_config(args, n):
                         (args.L, 2 * (args.L - 2), args.chi, args.lanczos_N),
             'L': args.L, 'chi': args.chi, 'lanczos_N': args.lanczos_N,
             'matvec_order': "auto ('split' for theta blocks >= 2^20 elements: LP, W0 W1, RP applied to the split theta, "
-                            "4 D d^2 chi^3 flop instead of the reference default's 4 D d^3 chi^3; same result)",
+                            "4 D d^2 chi^3 flop instead of the reference default's 4 D d^3 chi^3; same result); the "
+                            "identity components LP[IdL] = RP[IdR] = 1 of the environments (checked per bond) are not "
+                            "multiplied: 4 (D-1) d^2 chi^3 flop in the two large GEMMs",
             'parallelism': 'independent DMRG runs (field scan g=1+0.02*rank), %d rank(s)' % n,
             'l2': 'working set per step (100 x (LP, RP, B) ~ 7 GB) >> 126 MB L2; no explicit flush'}
 
@@ -442,6 +444,7 @@ def matvec_order_probe(eng, psi, L, chi, d, D, reps=5):
         i0 = L // 2 - 1
         for order in ('combined', 'split'):
             H = TwoSiteH(eng.env, i0, combine=True, matvec_order=order)
+            H.identity_env = False          # plain contraction orders; the sweep's route is timed by the sweep itself
             theta = H.combine_theta(psi.get_theta(i0, 2))
             for _ in range(3):
                 H.matvec(theta)
@@ -455,7 +458,10 @@ def matvec_order_probe(eng, psi, L, chi, d, D, reps=5):
             ms = ev0.elapsed_time(ev1) / reps
             executed = 4. * D * d**3 * chi**3 if order == 'combined' else 4. * D * d**2 * chi**3
             out[order] = {'ms_per_matvec': ms, 'executed_flop': executed, 'executed_tflops': executed / ms / 1e9,
-                          'reference_equivalent_tflops': 4. * D * d**3 * chi**3 / ms / 1e9}
+                          'reference_equivalent_tflops': 4. * D * d**3 * chi**3 / ms / 1e9,
+                          # the probe's environments are contracted from the chain end through inverse Schmidt values and
+                          # are not canonical, so the identity-component shortcut of the sweep is normally off here
+                          'identity_env_used': bool(getattr(H, '_id_env', False))}
             del H, theta
         out['auto_selects'] = 'split' if TwoSiteH(eng.env, i0, combine=True)._use_split(
             TwoSiteH(eng.env, i0, combine=True).combine_theta(psi.get_theta(i0, 2))) else 'combined'

@@ -9,7 +9,7 @@ whole process without code changes, so that the first GPU call of a round can A/
 name        effect
 =========== =========================================================================================
 fused       TwoSiteH.mpo_apply = 'fused'            (b200_mid_contract_f64 / b200_mid_contract2_f64)
-identity    TwoSiteH.identity_env = True             (skip LP[IdL], RP[IdR] in the split-order matvec)
+identity    TwoSiteH.identity_env = True             (default since the end of round 1; B200_OPTINS name kept)
 devscal     Lanczos option device_scalars = True     (b200_lanczos_update_dev_f64, b200_scal_rsqrt_dev_f64)
 eigv2       b200_svd_set_eig_variant(2)              (jacobi_eig_kernel_v2)
 qrhh        np_conserved.qr_method = 'householder'   (b200_block_qr_f64)

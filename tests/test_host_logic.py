@@ -265,6 +265,7 @@ def test_matvec_split_order_equals_combined(fake_device):
         for i0 in range(L - 1):
             Hc = TwoSiteH(eng.env, i0, combine=True, matvec_order='combined')
             Hs = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+            Hs.identity_env = False      # the contraction order alone (the identity shortcut: test_matvec_identity_env)
             theta = Hc.combine_theta(psi.get_theta(i0, 2))
             a, b = Hc.matvec(theta), Hs.matvec(theta)
             assert a.get_leg_labels() == b.get_leg_labels()
@@ -312,6 +313,7 @@ def test_matvec_fused_mpo_apply(fake_device):
     for i0 in range(7):
         Ht = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
         Hf = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+        Ht.identity_env = Hf.identity_env = False      # b200_mid_contract_f64 (the two-segment kernel: identity test)
         Hf.mpo_apply = 'fused'
         theta = Ht.combine_theta(psi.get_theta(i0, 2))
         n0 = fake_device.calls.get('mid_contract', 0)
@@ -390,6 +392,7 @@ def test_split_matvec_shares_buffers_without_charges(fake_device):
     eng.sweep()
     eng.sweep()
     H = TwoSiteH(eng.env, 3, combine=True, matvec_order='split')
+    H.identity_env = False
     theta = H.combine_theta(psi.get_theta(3, 2))
     before = theta.to_ndarray().copy()
     H.matvec(theta)                                   # plans cached now
