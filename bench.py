@@ -341,6 +341,23 @@ def run_b200(args):
     from tenpy_b200.linalg.truncation import subspace_stats as sub_stats
     jsw = svd_stats['jacobi_sweeps'][-2 * (L - 2):]
 
+    # ---- A/B of the identity-environment shortcut of the matvec (same state, same work otherwise): one sweep without it
+    ab = {}
+    if rank == 0 or world == 1:
+        try:
+            eng.options['identity_env'] = False
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a0.record()
+            eng.sweep()
+            a1.record()
+            torch.cuda.synchronize()
+            ab['sweep_s_identity_env_off'] = a0.elapsed_time(a1) / 1e3
+        except Exception as e:   # never lose the bench line
+            ab['error'] = repr(e)
+        finally:
+            eng.options.pop('identity_env', None)
+
     # ---- one more sweep with per-family CUDA-event profiling (after the timed one: same, converged regime; the
     #      event pairs bracket every library call, so host gaps inside a call -- the SVD reads q doubles per Jacobi
     #      sweep -- count for that family)
@@ -403,7 +420,7 @@ def run_b200(args):
             'roofline': roofline, 'roofline_gemm': roof['gemm'], 'roofline_svd': roof['svd'],
             'kernel_time_shares': shares, 'kernel_family_ms_per_sweep': {k: round(v[1], 2) for k, v in prof.items()},
             'matvec_orders': mv_orders, 'matvec_gflops': _matvec_gflops(mv_orders),
-            'blocksparse_matvec': bs_probes, 'peaks': peaks_kind,
+            'blocksparse_matvec': bs_probes, 'ab': ab, 'peaks': peaks_kind,
             'result': {'E': [float(x) for x in allst[:, 1]], 'S_mid': [float(x) for x in allst[:, 2]],
                        'N_lanczos_mean': N_lan, 'svd_jacobi_sweeps_mean': float(np.mean(jsw)),
                        'svd_jacobi_sweeps_max': int(np.max(jsw)), 'svd_calls': svd_stats['calls'],
