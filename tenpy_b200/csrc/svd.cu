@@ -33,7 +33,6 @@ constexpr int JKC = 128;        // streamed chunk (columns)
 constexpr int JLDP = JKC + 4;   // smem row stride of a panel chunk
 constexpr int JTHREADS = 256;
 constexpr int JLDG = JP + 1;
-constexpr int JLDQT = JP + 4;
 constexpr int J_NSPLIT_MAX = 16;    // column splits of the streaming phases of one pair
 constexpr int J_INNER_SWEEPS = 2;   // the pivot block only has to be diagonalised "well enough" per round: the outer sweep
                                     // count is the same for 2 and 4 (profiles/jacobi_sweeps_study.md; 4 until round 1)
