@@ -222,8 +222,14 @@ class TwoSiteH:
         if self._W01 is None:
             self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])   # wL p0 p0* p1 p1* wR  (D^2 d^4 numbers)
         th = theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)            # vL p0 p1 vR (read only here)
-        if self.identity_env and self._identity_env_setup():
-            return self._matvec_split_identity(th, labels)
+        if self.identity_env and getattr(self, '_id_env', None) is not False:
+            try:
+                if self._identity_env_setup():
+                    return self._matvec_split_identity(th, labels)
+            except Exception as e:       # a shortcut must never take the matvec down: plain split order from here on
+                import logging
+                logging.getLogger(__name__).warning('identity_env shortcut disabled for bond %d: %r', self.i0, e)
+                self._id_env = False
         th = npc.tensordot(self.LP, th, axes=['vR', 'vL'])                   # vR* wR p0 p1 vR      2 D d^2 chi^3
         fused = self._apply_W01_fused(th) if self.mpo_apply == 'fused' else None
         if fused is not None:
