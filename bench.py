@@ -341,6 +341,9 @@ def run_b200(args):
     from tenpy_b200.linalg.truncation import subspace_stats as sub_stats
     jsw = svd_stats['jacobi_sweeps'][-2 * (L - 2):]
 
+    from tenpy_b200.algorithms.mps_common import TwoSiteH as _H2
+    id_stats = dict(_H2.stats)      # bonds of all sweeps so far on which the identity-environment shortcut applied
+
     # ---- A/B of the identity-environment shortcut of the matvec (same state, same work otherwise): one sweep without it
     ab = {}
     if rank == 0 or world == 1:
@@ -420,7 +423,7 @@ def run_b200(args):
             'roofline': roofline, 'roofline_gemm': roof['gemm'], 'roofline_svd': roof['svd'],
             'kernel_time_shares': shares, 'kernel_family_ms_per_sweep': {k: round(v[1], 2) for k, v in prof.items()},
             'matvec_orders': mv_orders, 'matvec_gflops': _matvec_gflops(mv_orders),
-            'blocksparse_matvec': bs_probes, 'ab': ab, 'peaks': peaks_kind,
+            'blocksparse_matvec': bs_probes, 'ab': ab, 'identity_env_stats': id_stats, 'peaks': peaks_kind,
             'result': {'E': [float(x) for x in allst[:, 1]], 'S_mid': [float(x) for x in allst[:, 2]],
                        'N_lanczos_mean': N_lan, 'svd_jacobi_sweeps_mean': float(np.mean(jsw)),
                        'svd_jacobi_sweeps_max': int(np.max(jsw)), 'svd_calls': svd_stats['calls'],

@@ -184,6 +184,7 @@ class TwoSiteH:
     # skip the identity components of the environments in the split-order matvec (see _identity_env_setup): host logic on
     # the GPU-verified kernels, results checked against the reference goldens; engine option `identity_env` switches it off
     identity_env = True
+    stats = {'identity_env_bonds': 0, 'identity_env_rejected': 0}     # diagnostics (how often the shortcut applied)
 
     def __init__(self, env, i0, combine=False, move_right=True, matvec_order='auto'):
         if matvec_order not in ('auto', 'combined', 'split'):
@@ -250,6 +251,12 @@ class TwoSiteH:
         if getattr(self, '_id_env', None) is not None:
             return self._id_env
         self._id_env = False
+        ok = self._identity_env_prepare()
+        TwoSiteH.stats['identity_env_bonds' if ok else 'identity_env_rejected'] += 1
+        self._id_env = ok
+        return ok
+
+    def _identity_env_prepare(self):
         H = getattr(self, '_H_mpo', None)
         if H is None:
             return False
@@ -287,7 +294,6 @@ class TwoSiteH:
         W_rest, W_one = pieces(W01p, 'wR', only_r)
         self._W01p = npc.concatenate([W_rest, W_one], axis='wR')             # wR: [others ..., IdR]
         self._mask_rest_r = np.arange(D_r) < D_r - 1
-        self._id_env = True
         return True
 
     def _matvec_split_identity(self, th, labels):
