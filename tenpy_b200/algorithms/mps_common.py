@@ -312,14 +312,44 @@ class TwoSiteH:
         th_id = th.add_leg(self._leg_IdL, 0, axis=1, label='wR').ireplace_label('vL', 'vR*')
         t1 = npc.concatenate([t1, th_id], axis='wR')                         # wR: [others ..., IdL]
         t2 = npc.tensordot(t1, self._W01p, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])   # vR* vR p0 p1 wR
-        direct = t2.take_slice(len(self._mask_rest_r) - 1, 'wR')            # component IdR: no contraction with RP
-        t2.iproject(self._mask_rest_r, 'wR')
+        views = self._split_t2_views(t2)
+        if views is not None:            # no charges: the two components are the two blocks of t2, shared not copied
+            t2, direct = views
+        else:
+            direct = t2.take_slice(len(self._mask_rest_r) - 1, 'wR')        # component IdR: no contraction with RP
+            t2.iproject(self._mask_rest_r, 'wR')
         out = npc.tensordot(t2, self._RP_rest, axes=[['vR', 'wR'], ['vL', 'wL']])   # vR* p0 p1 vL*  2 (D-1) d^2 chi^3
         out.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
         direct.ireplace_label('vR*', 'vL').itranspose(out.get_leg_labels())
         out.iadd_prefactor_other(1., direct)
         out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
         return out.itranspose(labels)
+
+    @staticmethod
+    def _split_t2_views(t2):
+        """``t2[vR*, vR, p0, p1, wR]`` with the MPO leg in two sectors [others, IdR] and no other sector structure: the two
+        stored blocks ARE the two components.  Returns read-only views ``(t2_rest, direct)`` sharing the packed buffer
+        (`direct` without its unit MPO leg), or None if the structure is different (charged tensors)."""
+        lay = t2._layout
+        leg = t2.legs[-1]
+        if lay.nblocks != 2 or lay.has_padding or leg.block_number != 2 or np.any(lay.qdata[:, :-1] != 0) or \
+                list(lay.qdata[:, -1]) != [0, 1] or int(lay.shapes[1, -1]) != 1 or t2.get_leg_labels()[-1] != 'wR' or \
+                any(l.block_number != 1 for l in t2.legs[:-1]):
+            return None
+        from ..linalg.charges import LegCharge
+        chinfo = t2.chinfo
+        leg_rest = LegCharge.from_qind(chinfo, leg.slices[:2], leg.charges[:1], leg.qconj)
+        if np.any(chinfo.make_valid(leg.get_charge(0)) != 0) or np.any(chinfo.make_valid(leg.get_charge(1)) != 0):
+            return None
+        n0, n1 = int(lay.sizes[0]), int(lay.sizes[1])
+        o0, o1 = int(lay.offsets[0]), int(lay.offsets[1])
+        rest = npc.Array(t2.legs[:-1] + [leg_rest], np.float64, t2.qtotal, t2.get_leg_labels())
+        lay_r = npc.BlockLayout(np.zeros((1, t2.rank), np.int64), lay.shapes[:1])
+        rest._set_blocks(lay_r, t2._buf[o0:o0 + n0])
+        direct = npc.Array(t2.legs[:-1], np.float64, t2.qtotal, t2.get_leg_labels()[:-1])
+        lay_d = npc.BlockLayout(np.zeros((1, t2.rank - 1), np.int64), lay.shapes[1:2, :-1])
+        direct._set_blocks(lay_d, t2._buf[o1:o1 + n1])
+        return rest, direct
 
     def _apply_W01_fused_identity(self, t1, th):
         """``[Y_rest; Y_IdR] = (W0 W1) . [T1_rest; theta]`` in one streaming pass (b200_mid_contract2_f64): both inputs

@@ -450,6 +450,10 @@ def test_matvec_identity_env(fake_device):
             Hi.identity_env = True
             theta = Hc.combine_theta(psi.get_theta(i0, 2))
             a, b = Hc.matvec(theta), Hi.matvec(theta)
+            if mixer is None and Hi._id_env:      # no charges: the two components of t2 are shared views, nothing is gathered
+                n_take = fake_device.calls.get('take_blocks', 0)
+                Hi.matvec(theta)
+                assert fake_device.calls.get('take_blocks', 0) == n_take
             used += int(bool(Hi._id_env))
             assert a.get_leg_labels() == b.get_leg_labels()
             assert npc.norm(a - b) <= 1e-11 * max(npc.norm(a), 1e-300), (i0, npc.norm(a - b), npc.norm(a))
