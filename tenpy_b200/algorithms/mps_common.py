@@ -327,27 +327,31 @@ class TwoSiteH:
 
     @staticmethod
     def _split_t2_views(t2):
-        """``t2[vR*, vR, p0, p1, wR]`` with the MPO leg in two sectors [others, IdR] and no other sector structure: the two
+        """``t2`` (legs ``vR*, vR, p0, wR, p1``) with the MPO leg in two sectors [others, IdR] and no other sector structure: the two
         stored blocks ARE the two components.  Returns read-only views ``(t2_rest, direct)`` sharing the packed buffer
         (`direct` without its unit MPO leg), or None if the structure is different (charged tensors)."""
         lay = t2._layout
-        leg = t2.legs[-1]
-        if lay.nblocks != 2 or lay.has_padding or leg.block_number != 2 or np.any(lay.qdata[:, :-1] != 0) or \
-                list(lay.qdata[:, -1]) != [0, 1] or int(lay.shapes[1, -1]) != 1 or t2.get_leg_labels()[-1] != 'wR' or \
-                any(l.block_number != 1 for l in t2.legs[:-1]):
+        ax = t2.get_leg_index('wR')
+        leg = t2.legs[ax]
+        others = [a for a in range(t2.rank) if a != ax]
+        if lay.nblocks != 2 or lay.has_padding or leg.block_number != 2 or np.any(lay.qdata[:, others] != 0) or \
+                list(lay.qdata[:, ax]) != [0, 1] or int(lay.shapes[1, ax]) != 1 or \
+                any(t2.legs[a].block_number != 1 for a in others):
             return None
         from ..linalg.charges import LegCharge
         chinfo = t2.chinfo
-        leg_rest = LegCharge.from_qind(chinfo, leg.slices[:2], leg.charges[:1], leg.qconj)
         if np.any(chinfo.make_valid(leg.get_charge(0)) != 0) or np.any(chinfo.make_valid(leg.get_charge(1)) != 0):
             return None
+        leg_rest = LegCharge.from_qind(chinfo, leg.slices[:2], leg.charges[:1], leg.qconj)
         n0, n1 = int(lay.sizes[0]), int(lay.sizes[1])
         o0, o1 = int(lay.offsets[0]), int(lay.offsets[1])
-        rest = npc.Array(t2.legs[:-1] + [leg_rest], np.float64, t2.qtotal, t2.get_leg_labels())
+        legs_r = list(t2.legs)
+        legs_r[ax] = leg_rest
+        rest = npc.Array(legs_r, np.float64, t2.qtotal, t2.get_leg_labels())
         lay_r = npc.BlockLayout(np.zeros((1, t2.rank), np.int64), lay.shapes[:1])
         rest._set_blocks(lay_r, t2._buf[o0:o0 + n0])
-        direct = npc.Array(t2.legs[:-1], np.float64, t2.qtotal, t2.get_leg_labels()[:-1])
-        lay_d = npc.BlockLayout(np.zeros((1, t2.rank - 1), np.int64), lay.shapes[1:2, :-1])
+        direct = npc.Array([t2.legs[a] for a in others], np.float64, t2.qtotal, [t2.get_leg_labels()[a] for a in others])
+        lay_d = npc.BlockLayout(np.zeros((1, t2.rank - 1), np.int64), lay.shapes[1:2, others])
         direct._set_blocks(lay_d, t2._buf[o1:o1 + n1])
         return rest, direct
 
