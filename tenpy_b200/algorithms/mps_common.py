@@ -299,6 +299,17 @@ class TwoSiteH:
     def _matvec_split_identity(self, th, labels):
         """Split-order matvec without the identity components of the environments: ``T1 = [LP_rest . theta, theta]``,
         ``T2 = (W0 W1) . T1``, ``result = T2[rest] . RP_rest + T2[IdR]``."""
+        cat = getattr(self, '_t1_cat', None)
+        if cat is not None and self.mpo_apply != 'fused' and th._layout is cat[3]:
+            # no charges: GEMM 1 writes straight into the first block of the packed [LP_rest . theta, theta], theta is
+            # copied behind it (no add_leg / concatenate launches)
+            lay_cat, legs_cat, n0, _ = cat
+            from .. import backend
+            buf = backend.empty(lay_cat.size)
+            npc.tensordot(self._LP_rest, th, axes=['vR', 'vL'], _out=buf[:n0])
+            buf[n0:].copy_(th._buf[:lay_cat.size - n0])
+            t1 = npc.Array(legs_cat, np.float64, th.qtotal, ['vR*', 'wR', 'p0', 'p1', 'vR'])._set_blocks(lay_cat, buf)
+            return self._matvec_split_identity_tail(t1, labels)
         t1 = npc.tensordot(self._LP_rest, th, axes=['vR', 'vL'])             # vR* wR' p0 p1 vR   2 (D-1) d^2 chi^3
         if self.mpo_apply == 'fused':
             fused = self._apply_W01_fused_identity(t1, th)
@@ -309,8 +320,18 @@ class TwoSiteH:
                 out.iadd_prefactor_other(1., y_id.ireplace_label('vR*', 'vL'))
                 out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
                 return out.itranspose(labels)
+        n0_single = int(t1._layout.size) if (t1._layout.nblocks == 1 and not t1._layout.has_padding) else None
         th_id = th.add_leg(self._leg_IdL, 0, axis=1, label='wR').ireplace_label('vL', 'vR*')
         t1 = npc.concatenate([t1, th_id], axis='wR')                         # wR: [others ..., IdL]
+        lay = t1._layout
+        if n0_single is not None and th._layout.nblocks == 1 and not th._layout.has_padding and lay.nblocks == 2 and \
+                not lay.has_padding and list(lay.offsets) == [0, n0_single] and int(lay.sizes[1]) == int(th._layout.size) \
+                and t1.get_leg_labels() == ['vR*', 'wR', 'p0', 'p1', 'vR']:
+            self._t1_cat = (lay, list(t1.legs), n0_single, th._layout)      # structure for the direct-write path
+        return self._matvec_split_identity_tail(t1, labels)
+
+    def _matvec_split_identity_tail(self, t1, labels):
+        """second half of :meth:`_matvec_split_identity`: ``(W0 W1) . T1``, contraction with `RP_rest`, identity part"""
         t2 = npc.tensordot(t1, self._W01p, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])   # vR* vR p0 p1 wR
         views = self._split_t2_views(t2)
         if views is not None:            # no charges: the two components are the two blocks of t2, shared not copied

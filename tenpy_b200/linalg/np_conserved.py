@@ -1081,11 +1081,13 @@ def _prepare_contraction(a, b, axes):
     return a, b, n
 
 
-def tensordot(a, b, axes=2):
+def tensordot(a, b, axes=2, _out=None):
     """Contract legs of `a` with legs of `b`, like ``np.tensordot`` (reference npc:3612).
 
     The block products of the whole contraction run as ONE grouped FP64 tensor-core GEMM launch per tile
-    shape (worker: reference pyx:1498 / npc:4846)."""
+    shape (worker: reference pyx:1498 / npc:4846).  ``_out`` (internal): device buffer of exactly the result's packed
+    size without alignment padding, written instead of a fresh allocation (lets a caller place the result inside a
+    larger packed buffer)."""
     a, b, n = _prepare_contraction(a, b, axes)
     cut_a = a.rank - n
     if cut_a == 0 and b.rank == n:
@@ -1119,7 +1121,12 @@ def tensordot(a, b, axes=2):
     plan, lay_c = cached[2], cached[3]
     if lay_c is None:
         return res
-    buf = backend.zeros(lay_c.size) if lay_c.has_padding else backend.empty(lay_c.size)
+    if _out is not None:
+        if lay_c.has_padding or _out.numel() != lay_c.size:
+            raise ValueError('tensordot(_out=...): buffer does not fit the result layout')
+        buf = _out
+    else:
+        buf = backend.zeros(lay_c.size) if lay_c.has_padding else backend.empty(lay_c.size)
     plan.run(a._buf, b._buf, buf)
     res._set_blocks(lay_c, buf)
     return res

@@ -452,8 +452,10 @@ def test_matvec_identity_env(fake_device):
             a, b = Hc.matvec(theta), Hi.matvec(theta)
             if mixer is None and Hi._id_env:      # no charges: the two components of t2 are shared views, nothing is gathered
                 n_take = fake_device.calls.get('take_blocks', 0)
-                Hi.matvec(theta)
+                c = Hi.matvec(theta)     # second call: GEMM 1 writes straight into the packed [LP_rest.theta, theta]
                 assert fake_device.calls.get('take_blocks', 0) == n_take
+                assert getattr(Hi, '_t1_cat', None) is not None
+                assert npc.norm(c - b) <= 1e-14 * max(npc.norm(b), 1e-300)
             used += int(bool(Hi._id_env))
             assert a.get_leg_labels() == b.get_leg_labels()
             assert npc.norm(a - b) <= 1e-11 * max(npc.norm(a), 1e-300), (i0, npc.norm(a - b), npc.norm(a))
