@@ -270,3 +270,59 @@ def test_full_size_properties(gpu_lib):
     assert np.max(np.abs(G - np.eye(G.shape[0]))) < 1e-11
     Sref = np.linalg.svd(th.to_ndarray(), compute_uv=False)
     assert np.max(np.abs(S - Sref)) < 1e-8 * Sref[0]
+
+
+@pytest.mark.gpu
+def test_split_and_identity_matvec_routes(gpu_lib):
+    """The contraction routes the benchmark takes for large blocks, forced here on small ones: 'split' order (LP, W0 W1, RP on
+    the split theta), the identity-environment shortcut (LP[IdL] = RP[IdR] = 1 skipped, views / direct write in the dense
+    case) -- per bond against the reference's combined sequence, and whole DMRG runs against the reference's energies."""
+    from tenpy_b200.models import TFIChain, SpinChain, FermiHubbardChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg import np_conserved as npc
+    cases = [(TFIChain({'L': 8, 'J': 1., 'g': 1.1, 'conserve': None}), ['up'] * 8, None),
+             (SpinChain({'L': 8, 'Jx': 1., 'Jy': 1., 'Jz': 0.7, 'conserve': 'Sz'}), ['up', 'down'] * 4, True),
+             (FermiHubbardChain({'L': 6, 't': 1., 'U': 4., 'mu': 0.}), ['up', 'down'] * 3, True)]
+    for M, state, mixer in cases:
+        psi = MPS.from_product_state(M.lat_sites, state)
+        eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': mixer, 'combine': True, 'matvec_order': 'combined',
+                                              'trunc_params': {'chi_max': 24, 'svd_min': 1e-12}})
+        eng.sweep()
+        eng.sweep()
+        eng.mixer_cleanup()
+        psi.canonical_form()
+        eng.env.clear()
+        used = 0
+        for i0 in range(psi.L - 1):
+            Hc = TwoSiteH(eng.env, i0, combine=True, matvec_order='combined')
+            Hs = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+            Hs.identity_env = False
+            Hi = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
+            Hi.identity_env = True
+            theta = Hc.combine_theta(psi.get_theta(i0, 2))
+            before = theta.to_ndarray().copy()
+            a, b, c = Hc.matvec(theta), Hs.matvec(theta), Hi.matvec(theta)
+            c2 = Hi.matvec(theta)                      # second call: cached structures / direct-write path
+            scale = max(npc.norm(a), 1e-300)
+            assert npc.norm(a - b) <= 1e-13 * scale
+            assert npc.norm(a - c) <= 1e-11 * scale and npc.norm(c - c2) <= 1e-14 * scale
+            assert np.array_equal(theta.to_ndarray(), before)       # the views never write into the input
+            used += int(bool(Hi._id_env))
+        assert used >= 1        # (how often it applies on the device is reported by bench.py: identity_env_stats)
+    g = h.load('dmrg.npz')
+    M = TFIChain({'L': 20, 'J': 1., 'g': 1., 'conserve': None})
+    psi = MPS.from_product_state(M.lat_sites, ['up'] * 20)
+    res = dmrg.run(psi, M, {'mixer': None, 'max_E_err': 1e-10, 'combine': True, 'matvec_order': 'split',
+                            'identity_env': True, 'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
+    assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
+    assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
+    L = 16
+    M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 1., 'conserve': 'Sz'})
+    psi = MPS.from_product_state(M.lat_sites, ['up', 'down'] * (L // 2))
+    res = dmrg.run(psi, M, {'mixer': True, 'mixer_params': {'amplitude': 1e-5, 'decay': 2., 'disable_after': 6},
+                            'max_E_err': 1e-11, 'max_S_err': 1e-8, 'trunc_params': {'chi_max': 60, 'svd_min': 1e-10},
+                            'combine': True, 'max_sweeps': 20, 'matvec_order': 'split', 'identity_env': True})
+    assert abs(res['E'] - g['xxz_E']) < 1e-10 * abs(g['xxz_E'])
+    assert np.max(np.abs(psi.entanglement_entropy() - g['xxz_S'])) < 1e-7
