@@ -58,9 +58,12 @@ def main():
     eng.mixer_deactivate()
     times = []
     fam = {}
+    from tenpy_b200.linalg import np_conserved as npc_mod
+    plans_before, wall_last = 0, None
     for k in range(args.timed):
         if k == args.timed - 1 and cuda:
             lib.profile = {}
+            plans_before = len(npc_mod._PLAN_CACHE)
         if cuda:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -69,10 +72,30 @@ def main():
         if cuda:
             ev1.record()
         lib.synchronize()
+        wall_last = time.perf_counter() - t0
         times.append(ev0.elapsed_time(ev1) / 1e3 if cuda else time.perf_counter() - t0)
+    detail = {}
     if cuda and lib.profile is not None:
         fam = {k: round(v[1], 1) for k, v in lib.profile_summary().items()}
+        det = lib.profile_detail()
         lib.profile = None
+        # contraction efficiency by size class: where does the GEMM family time go?
+        g = [(ms, info) for ms, info in det.get('gemm', []) if info]
+        bins = [(0, 1e6), (1e6, 1e7), (1e7, 1e8), (1e8, 1e9), (1e9, 1e10), (1e10, 1e13)]
+        hist = []
+        for lo, hi in bins:
+            sel = [(ms, i) for ms, i in g if lo <= i[0] < hi]
+            if sel:
+                tms, tfl = sum(x[0] for x in sel), sum(x[1][0] for x in sel)
+                hist.append({'flop_range': [lo, hi], 'calls': len(sel), 'ms': round(tms, 2), 'gflop': round(tfl / 1e9, 2),
+                             'tflops': round(tfl / tms / 1e9, 3) if tms else None,
+                             'mean_pairs': round(float(np.mean([x[1][1] for x in sel])), 1)})
+        slow = sorted(g, key=lambda x: -x[0])[:8]
+        detail = {'gemm_by_flops': hist, 'gemm_slowest': [{'ms': round(ms, 3), 'flops': i[0], 'pairs': i[1], 'blocks_out': i[2]}
+                                                          for ms, i in slow],
+                  'calls': {k: len(v) for k, v in det.items()},
+                  'wall_s_last_sweep': wall_last, 'plan_cache_size': len(npc_mod._PLAN_CACHE),
+                  'plans_built_last_sweep': len(npc_mod._PLAN_CACHE) - plans_before}
     i0 = L // 2 - 1
     H = TwoSiteH(eng.env, i0, combine=True)
     theta = H.combine_theta(psi.get_theta(i0, 2))
@@ -86,7 +109,7 @@ def main():
                       'bond_sectors': int(psi.get_B(L // 2).get_leg('vL').block_number),
                       'N_lanczos_mean': float(np.mean(eng.update_stats['N_lanczos'][-nb:])),
                       'svd_jacobi_sweeps_mean': float(np.mean(svd_stats['jacobi_sweeps'][-nb:])),
-                      'family_ms_last_sweep': fam}))
+                      'family_ms_last_sweep': fam, 'detail': detail}))
 
 
 if __name__ == '__main__':

@@ -124,10 +124,10 @@ def _ptr(t):
 
 class _Prof:
     """records a CUDA-event pair around a library call when ``lib.profile`` is a dict (bench / profiling)."""
-    __slots__ = ('lib', 'cat', 'ev0')
+    __slots__ = ('lib', 'cat', 'ev0', 'info')
 
-    def __init__(self, lib, cat):
-        self.lib, self.cat, self.ev0 = lib, cat, None
+    def __init__(self, lib, cat, info=None):
+        self.lib, self.cat, self.ev0, self.info = lib, cat, None, info
 
     def __enter__(self):
         if self.lib.profile is not None:
@@ -139,7 +139,7 @@ class _Prof:
         if self.ev0 is not None:
             ev1 = self.lib.torch.cuda.Event(enable_timing=True)
             ev1.record()
-            self.lib.profile.setdefault(self.cat, []).append((self.ev0, ev1))
+            self.lib.profile.setdefault(self.cat, []).append((self.ev0, ev1, self.info))
         return False
 
 
@@ -179,7 +179,7 @@ class TdotPlan:
 
     def run(self, A, B, C):
         lib = self._lib
-        with _Prof(lib, 'gemm'):
+        with _Prof(lib, 'gemm', (self.flops, self.n_pairs, self.n_c)):
             lib._check(lib.c.b200_tdot_plan_run(self._h, _ptr(A), _ptr(B), _ptr(C), lib.stream()))
 
     def __del__(self):
@@ -212,8 +212,14 @@ class DeviceLib:
         self.synchronize()
         out = {}
         for cat, evs in (self.profile or {}).items():
-            out[cat] = (len(evs), float(sum(a.elapsed_time(b) for a, b in evs)))
+            out[cat] = (len(evs), float(sum(e[0].elapsed_time(e[1]) for e in evs)))
         return out
+
+    def profile_detail(self):
+        """{family: [(ms, info), ...]} of the collected event pairs (info: what the call site attached, e.g. the flops
+        and the number of block products of a contraction); synchronises."""
+        self.synchronize()
+        return {cat: [(float(e[0].elapsed_time(e[1])), e[2]) for e in evs] for cat, evs in (self.profile or {}).items()}
 
     # -- plumbing
     def stream(self):

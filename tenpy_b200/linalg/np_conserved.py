@@ -1512,9 +1512,12 @@ def _fill_null_vectors(lib, m, n, k, r, kf, transposed, bufU, u_off, bufV, v_off
 
 
 qr_stats = {'calls': 0, 'columns': 0, 'replaced': 0}   # diagnostics of the Gram-Schmidt QR
-# 'cgs2': Gram-Schmidt on the GEMM / BLAS-1 kernels (GPU-verified building blocks, one host round trip per column);
-# 'householder': b200_block_qr_f64, one launch for all blocks (host-checked, opt-in until it has run on a GPU)
-qr_method = 'cgs2'
+# 'householder': b200_block_qr_f64, one CTA per block, one launch for all blocks; 'cgs2': Gram-Schmidt on the GEMM /
+# BLAS-1 kernels (one host round trip per column); 'auto' (default): Householder for blocks up to QR_HOUSEHOLDER_MAX rows
+# or columns, Gram-Schmidt above.  Measured on the B200 (profiles/r02a_optins.md): 64x64 0.7 ms vs 17.3 ms, 300x130
+# 17.4 vs 37.5 ms, 512x512 207 vs 150 ms.
+qr_method = 'auto'
+QR_HOUSEHOLDER_MAX = 384
 
 
 def _block_qr_cgs2(lib, m, n, A, Q, R):
@@ -1630,10 +1633,12 @@ def qr(a, mode='reduced', inner_labels=[None, None], cutoff=None, pos_diag_R=Fal
         bufQ = backend.zeros(lay_Q.size)
         bufR = backend.zeros(lay_R.size)
         lib = backend.get_lib()
-        if qr_method == 'householder':
-            lib.block_qr(m, n, lay.offsets, q_off, r_off, a._buf, bufQ, bufR)
-        else:
-            for b in range(lay.nblocks):
+        small = np.ones(lay.nblocks, bool) if qr_method == 'householder' else \
+            (np.maximum(m, n) <= QR_HOUSEHOLDER_MAX if qr_method == 'auto' else np.zeros(lay.nblocks, bool))
+        if np.any(small):
+            lib.block_qr(m[small], n[small], lay.offsets[small], q_off[small], r_off[small], a._buf, bufQ, bufR)
+        if not np.all(small):
+            for b in np.nonzero(~small)[0]:
                 mb, nb, kb = int(m[b]), int(n[b]), int(k[b])
                 ao = int(lay.offsets[b])
                 _block_qr_cgs2(lib, mb, nb, a._buf[ao:ao + mb * nb], bufQ[int(q_off[b]):int(q_off[b]) + mb * kb],

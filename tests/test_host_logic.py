@@ -314,7 +314,7 @@ def test_matvec_fused_mpo_apply(fake_device):
         Ht = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
         Hf = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
         Ht.identity_env = Hf.identity_env = False      # b200_mid_contract_f64 (the two-segment kernel: identity test)
-        Hf.mpo_apply = 'fused'
+        Ht.mpo_apply, Hf.mpo_apply = 'tensordot', 'fused'
         theta = Ht.combine_theta(psi.get_theta(i0, 2))
         n0 = fake_device.calls.get('mid_contract', 0)
         a, b = Ht.matvec(theta), Hf.matvec(theta)
