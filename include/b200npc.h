@@ -105,6 +105,30 @@ int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m_host, const int64_t 
                           const int64_t *k_host, const int64_t *a_off_host, const int64_t *b_off_host,
                           const double *A, const double *B, double *C, b200_stream_t stream);
 
+/* ---- FP64 products on the int8 tensor path (tcgen05.mma kind::i8, accumulators in tensor memory) --------------------- */
+/* Ozaki splitting: each operand is cut into `slices` signed 7-bit digit planes (row-wise power-of-two scaling), the slice
+ * products are exact int8 x int8 -> int32 tensor-core GEMMs fed by bulk async copies (TMA unit), the diagonals are summed
+ * in FP64.  slices = 7: error ~1e-14 (|A||B|)_ij (Lanczos matvec), 8: FP64 rounding level.  Used by npc.tensordot for
+ * large dense block products; replaces the dgemm of CblasGemmBatch.run pyx:204-274 there.
+ * A split operand is an opaque device buffer of b200_ozaki_split_worksize(rows, k, slices) bytes holding a (rows x k)
+ * matrix whose element (r, kk) is X[r*ld_row + kk*ld_k] (one of the two strides must be 1): pass (lda, 1) for the left
+ * operand A (m x k, row-major) and (1, ldb) for the right operand B (k x n, row-major; rows = n).  Split operands can be
+ * reused across products (the environments of a bond across all Lanczos iterations). */
+int64_t b200_ozaki_split_worksize(int64_t rows, int64_t k, int32_t slices);
+int b200_ozaki_split_f64(int64_t rows, int64_t k, const double *X, int64_t ld_row, int64_t ld_k, int32_t slices,
+                         void *out_dev, int64_t out_bytes, b200_stream_t stream);
+/* C (m x n, row-major, ldc) = (accumulate ? C : 0) + A . B from two split operands with the same k and slice count */
+int b200_ozaki_mm_f64(int64_t m, int64_t n, int64_t k, int32_t slices, const void *a_split, const void *b_split,
+                      double *C, int64_t ldc, int32_t accumulate, b200_stream_t stream);
+/* split both operands into `work_dev` (b200_ozaki_gemm_worksize bytes) and multiply */
+int64_t b200_ozaki_gemm_worksize(int64_t m, int64_t n, int64_t k, int32_t slices);
+int b200_ozaki_gemm_f64(int64_t m, int64_t n, int64_t k, const double *A, int64_t lda, const double *B, int64_t ldb,
+                        double *C, int64_t ldc, int32_t slices, int32_t accumulate, void *work_dev, int64_t work_bytes,
+                        b200_stream_t stream);
+/* every pipeline wait of the tensor-core kernel has a watchdog; returns B200_ERR_CUDA if one fired since the last call
+ * (synchronises; for tests and debugging, never needed in a correct run) */
+int b200_ozaki_check_abort(void);
+
 /* ---- BLAS-1 on packed block buffers (Lanczos vector ops) ------------------------------------------ */
 /* y += alpha x.  replaces Array.iadd_prefactor_other npc:2373 / pyx:860 (daxpy pyx:328-335) */
 int b200_axpy_f64(int64_t n, double alpha, const double *X, double *Y, b200_stream_t stream);

@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
 }
 
 // rate probe: tiles resident, `iters` x 4 MMAs (K = 32 each) back to back into `nacc` accumulators round robin
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int nacc, int *abort_flag, int32_t *sink) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int nacc, int *abort_flag, int32_t *sink, int layout,
+                                                      uint32_t lbo, uint32_t sbo, uint32_t kstep, int nk) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem, *sB = smem + 128 * 128;
@@ -140,7 +141,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int nacc
             uint32_t d = tmem + (it % nacc) * N;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                mma_i8(d, smem_desc_sw128(a0 + k * 32), smem_desc_sw128(b0 + k * 32), idesc, it >= nacc ? 1u : (k ? 1u : 0u));
+                mma_i8(d, smem_desc(a0 + (k % nk) * kstep, lbo, sbo, layout), smem_desc(b0 + (k % nk) * kstep, lbo, sbo, layout), idesc,
+                       it >= nacc ? 1u : (k ? 1u : 0u));
         }
         mma_commit(&done);
     }
@@ -224,7 +226,8 @@ static int run_case(const char *name, int N, int KT, int layout, uint32_t lbo, u
     return (e == cudaSuccess && flag == 0 && bad == 0) ? 0 : 1;
 }
 
-static int run_rate(int N, int nacc, int ctas) {
+static int run_rate(int N, int nacc, int ctas, int layout = 2, uint32_t lbo = 16, uint32_t sbo = 1024, uint32_t kstep = 32, int nk = 4,
+                    const char *tag = "sw128") {
     int *dflag;
     int32_t *sink;
     CK(cudaMalloc(&dflag, 4));
@@ -236,10 +239,10 @@ static int run_rate(int N, int nacc, int ctas) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    rate_kernel<<<ctas, 128, smem>>>(N, 200, nacc, dflag, sink);
+    rate_kernel<<<ctas, 128, smem>>>(N, 200, nacc, dflag, sink, layout, lbo, sbo, kstep, nk);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    rate_kernel<<<ctas, 128, smem>>>(N, iters, nacc, dflag, sink);
+    rate_kernel<<<ctas, 128, smem>>>(N, iters, nacc, dflag, sink, layout, lbo, sbo, kstep, nk);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms;
@@ -247,7 +250,7 @@ static int run_rate(int N, int nacc, int ctas) {
     int flag;
     cudaMemcpy(&flag, dflag, 4, cudaMemcpyDeviceToHost);
     double macs = (double)ctas * iters * 4 * 128.0 * N * 32.0;
-    printf("rate N=%3d nacc=%d ctas=%3d : %.3f ms  %.1f Tops/s (2*MAC)  watchdog=%d\n", N, nacc, ctas, ms,
+    printf("rate %-22s N=%3d nacc=%d ctas=%3d : %.3f ms  %.1f Tops/s (2*MAC)  watchdog=%d\n", tag, N, nacc, ctas, ms,
            2 * macs / ms * 1e-9, flag);
     fflush(stdout);
     cudaFree(dflag);
@@ -277,6 +280,11 @@ int main(int argc, char **argv) {
         }
         run_rate(128, 4, 148);
         run_rate(256, 1, 296);
+        // un-swizzled core-matrix layouts and the 64-byte swizzle at N = 128 (the Ozaki kernel's tile shape)
+        run_rate(128, 4, 148, 0, 128, 1024, 256, 4, "interleave 128/1024");
+        run_rate(128, 4, 148, 0, 2048, 128, 4096, 2, "interleave 2048/128");
+        run_rate(128, 4, 148, 4, 16, 512, 32, 2, "sw64");
+        run_rate(128, 4, 148, 6, 16, 256, 32, 1, "sw32");
     }
     printf("probe %s (%d failing sw128 cases)\n", fails ? "FAILED" : "ok", fails);
     return fails ? 1 : 0;

@@ -65,6 +65,13 @@ _SIGNATURES = {
     'b200_block_qr_f64': (ctypes.c_int, [c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'b200_mid_contract2_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200_mid_contract_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'b200_ozaki_split_worksize': (c_i64, [c_i64, c_i64, c_i32]),
+    'b200_ozaki_split_f64': (ctypes.c_int, [c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp]),
+    'b200_ozaki_mm_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    'b200_ozaki_gemm_worksize': (c_i64, [c_i64, c_i64, c_i64, c_i32]),
+    'b200_ozaki_gemm_f64': (ctypes.c_int, [c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32,
+                                           c_vp, c_i64, c_vp]),
+    'b200_ozaki_check_abort': (ctypes.c_int, []),
     'b200_svd_set_deflation': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_eig_variant': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_eig_inner_sweeps': (ctypes.c_int, [ctypes.c_int]),
@@ -252,6 +259,28 @@ class DeviceLib:
         with _Prof(self, 'gemm'):
             self._check(self.c.b200_grouped_gemm_f64(len(ms[0]), ms[1], ns[1], cs[1], pp[1], len(ks[0]), ks[1], ao[1],
                                                      bo[1], _ptr(A), _ptr(B), _ptr(C), self.stream()))
+
+    # -- FP64 products on the int8 tensor path (csrc/ozaki.cu)
+    def ozaki_split(self, rows, k, X, ld_row, ld_k, slices):
+        """split a (rows x k) operand (element (r, kk) = X[r*ld_row + kk*ld_k]) into int8 digit planes; returns the
+        opaque device buffer (include/b200npc.h)"""
+        nbytes = int(self.c.b200_ozaki_split_worksize(int(rows), int(k), int(slices)))
+        if nbytes <= 0:
+            raise B200Error('ozaki_split: bad shape / slice count')
+        out = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
+        with _Prof(self, 'split'):
+            self._check(self.c.b200_ozaki_split_f64(int(rows), int(k), _ptr(X), int(ld_row), int(ld_k), int(slices),
+                                                    _ptr(out), nbytes, self.stream()))
+        return out
+
+    def ozaki_mm(self, m, n, k, slices, a_split, b_split, C, ldc, accumulate=False):
+        """C (m x n, ldc) (+)= A . B from two split operands (include/b200npc.h)"""
+        with _Prof(self, 'gemm', (2. * m * n * k, 1, 1)):
+            self._check(self.c.b200_ozaki_mm_f64(int(m), int(n), int(k), int(slices), _ptr(a_split), _ptr(b_split),
+                                                 _ptr(C), int(ldc), 1 if accumulate else 0, self.stream()))
+
+    def ozaki_check_abort(self):
+        self._check(self.c.b200_ozaki_check_abort())
 
     # -- BLAS-1
     def axpy(self, n, alpha, X, Y):

@@ -150,6 +150,12 @@ def _get_LHeff(env, i, eff_H):
     return env._contract_LHeff(i)
 
 
+def _mv_dot(a, b, axes, _out=None):
+    """`npc.tensordot` for the large products inside an effective-H matvec: on the int8 tensor path with the slice count
+    of the Lanczos iteration (``npc.OZAKI['slices_matvec']``, error ~1e-14 relative to (|A||B|)_ij per product)"""
+    return npc.tensordot(a, b, axes=axes, _out=_out, _oz_slices=npc.OZAKI['slices_matvec'])
+
+
 def _get_RHeff(env, i, eff_H):
     """`RHeff` with ``p1`` labels on site `i`, reusing the one of `eff_H` if it fits (reference :1893)."""
     if i == eff_H.i0 + eff_H.length - 1 and hasattr(eff_H, 'RHeff'):
@@ -232,13 +238,13 @@ class TwoSiteH:
                 import logging
                 logging.getLogger(__name__).warning('identity_env shortcut disabled for bond %d: %r', self.i0, e)
                 self._id_env = False
-        th = npc.tensordot(self.LP, th, axes=['vR', 'vL'])                   # vR* wR p0 p1 vR      2 D d^2 chi^3
+        th = _mv_dot(self.LP, th, axes=['vR', 'vL'])                          # vR* wR p0 p1 vR      2 D d^2 chi^3
         fused = self._apply_W01_fused(th) if self.mpo_apply == 'fused' else None
         if fused is not None:
-            th = npc.tensordot(fused, self._RP_t, axes=[['wR', 'vR'], ['wL', 'vL']])   # no transposition left
+            th = _mv_dot(fused, self._RP_t, axes=[['wR', 'vR'], ['wL', 'vL']])          # no transposition left
         else:
             th = npc.tensordot(th, self._W01, axes=[['wR', 'p0', 'p1'], ['wL', 'p0*', 'p1*']])  # vR* vR p0 p1 wR
-            th = npc.tensordot(th, self.RP, axes=[['vR', 'wR'], ['vL', 'wL']])   # vR* p0 p1 vL*   2 D d^2 chi^3
+            th = _mv_dot(th, self.RP, axes=[['vR', 'wR'], ['vL', 'wL']])          # vR* p0 p1 vL*   2 D d^2 chi^3
         th.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
         th = th.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)  # th is ours
         return th.itranspose(labels)
@@ -286,6 +292,8 @@ class TwoSiteH:
             return rest, one
         self._LP_rest, LP_one = pieces(LP, 'wR', only_l)
         self._RP_rest, RP_one = pieces(RP, 'wL', only_r)
+        # private copies, constant for the lifetime of this object: their int8 digit planes (npc.OZAKI) are made once
+        self._LP_rest._oz_const = self._RP_rest._oz_const = True
         self._leg_IdL = LP_one.get_leg('wR')     # unit legs carrying the charge of the identity component
         self._leg_IdR = RP_one.get_leg('wL')
         if self._W01 is None:
@@ -307,16 +315,16 @@ class TwoSiteH:
             lay_cat, legs_cat, n0, _ = cat
             from .. import backend
             buf = backend.empty(lay_cat.size)
-            npc.tensordot(self._LP_rest, th, axes=['vR', 'vL'], _out=buf[:n0])
+            _mv_dot(self._LP_rest, th, axes=['vR', 'vL'], _out=buf[:n0])
             buf[n0:].copy_(th._buf[:lay_cat.size - n0])
             t1 = npc.Array(legs_cat, np.float64, th.qtotal, ['vR*', 'wR', 'p0', 'p1', 'vR'])._set_blocks(lay_cat, buf)
             return self._matvec_split_identity_tail(t1, labels)
-        t1 = npc.tensordot(self._LP_rest, th, axes=['vR', 'vL'])             # vR* wR' p0 p1 vR   2 (D-1) d^2 chi^3
+        t1 = _mv_dot(self._LP_rest, th, axes=['vR', 'vL'])                    # vR* wR' p0 p1 vR   2 (D-1) d^2 chi^3
         if self.mpo_apply == 'fused':
             fused = self._apply_W01_fused_identity(t1, th)
             if fused is not None:
                 y_rest, y_id = fused                                         # vR* p0 p1 wR' vR ; vR* p0 p1 vR
-                out = npc.tensordot(y_rest, self._RP_rest_t, axes=[['wR', 'vR'], ['wL', 'vL']])
+                out = _mv_dot(y_rest, self._RP_rest_t, axes=[['wR', 'vR'], ['wL', 'vL']])
                 out.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
                 out.iadd_prefactor_other(1., y_id.ireplace_label('vR*', 'vL'))
                 out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
@@ -340,7 +348,7 @@ class TwoSiteH:
         else:
             direct = t2.take_slice(len(self._mask_rest_r) - 1, 'wR')        # component IdR: no contraction with RP
             t2.iproject(self._mask_rest_r, 'wR')
-        out = npc.tensordot(t2, self._RP_rest, axes=[['vR', 'wR'], ['vL', 'wL']])   # vR* p0 p1 vL*  2 (D-1) d^2 chi^3
+        out = _mv_dot(t2, self._RP_rest, axes=[['vR', 'wR'], ['vL', 'wL']])          # vR* p0 p1 vL*  2 (D-1) d^2 chi^3
         out.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
         direct.ireplace_label('vR*', 'vL').itranspose(out.get_leg_labels())
         out.iadd_prefactor_other(1., direct)
@@ -404,6 +412,7 @@ class TwoSiteH:
                                axis=1)
             self._M_id = backend.to_device(np.ascontiguousarray(M))
             self._RP_rest_t = self._RP_rest.transpose(['wL', 'vL', 'vL*'])
+            self._RP_rest_t._oz_const = True
             self._N1 = d0 * d1 * len(rest_r)
             self._fused_legs = (self._W01.get_leg('p0'), self._W01.get_leg('p1'), self._RP_rest.get_leg('wL').conj())
         N1, N2 = self._N1, K2

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
 
     // producer cursor
     int pp = task.pair_begin, pk = 0;
-    GemmPair cur = pairs[pp];
+    GemmPair cur = (pp < task.pair_end) ? pairs[pp] : GemmPair{0, 0, 0, 0};   // a task without pairs writes zeros
 
     auto load_stage = [&](int stage) {
         const int k = cur.k;
@@ -234,9 +234,78 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     }
 }
 
+// ---- thin block products: streaming kernels ---------------------------------------------------------------------------
+// Contractions over an un-bunched MPO leg (LP.W0 -> LHeff, W1.RP -> RHeff, reference mpo.py:3107-3126) are lists of block
+// products with k = 1 per pair, a handful of pairs per output block and ONE narrow side (n or m of a few elements), the
+// other side being chi_sector^2 long.  A 32 x 32 tensor-core tile computes ~3 % useful work there and the launch has
+// > 10^6 CTAs (measured: 50-110 ms per call at chi = 1024, profiles/r02b).  They are HBM-bound sums of a few scaled
+// vectors: one thread per element of the long side, the narrow operand read through the read-only path (same address
+// for the whole warp), coalesced on the long operand.
+constexpr int THIN_MAX = 8;      // narrow side <= THIN_MAX elements
+constexpr int THIN_KSUM = 64;    // sum of k over the pairs of the output block
+constexpr int THIN_ROWS = 256;   // elements of the long side per CTA
+
+// C (m x n), n <= THIN_MAX:  C[r, :] = sum_p sum_kk A_p[r, kk] B_p[kk, :]
+__global__ void __launch_bounds__(THIN_ROWS)
+    thin_n_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
+                  const GemmTile *__restrict__ tiles, const GemmTask *__restrict__ tasks, const GemmPair *__restrict__ pairs) {
+    const GemmTile tile = tiles[blockIdx.x];
+    const GemmTask task = tasks[tile.task];
+    const int64_t r = (int64_t)tile.tm * THIN_ROWS + threadIdx.x;
+    if (r >= task.m) return;
+    const int n = task.n;
+    double acc[THIN_MAX];
+#pragma unroll
+    for (int j = 0; j < THIN_MAX; ++j) acc[j] = 0.0;
+    for (int p = task.pair_begin; p < task.pair_end; ++p) {
+        const GemmPair pr = pairs[p];
+        const double *a = A + pr.a_off + r * pr.k;
+        const double *b = B + pr.b_off;
+        for (int kk = 0; kk < pr.k; ++kk) {
+            const double av = a[kk];
+#pragma unroll
+            for (int j = 0; j < THIN_MAX; ++j)
+                if (j < n) acc[j] = fma(av, __ldg(b + (int64_t)kk * n + j), acc[j]);
+        }
+    }
+    double *c = C + task.c_off + r * n;
+#pragma unroll
+    for (int j = 0; j < THIN_MAX; ++j)
+        if (j < n) c[j] = acc[j];
+}
+
+// C (m x n), m <= THIN_MAX:  C[:, c] = sum_p sum_kk A_p[:, kk] B_p[kk, c]
+__global__ void __launch_bounds__(THIN_ROWS)
+    thin_m_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
+                  const GemmTile *__restrict__ tiles, const GemmTask *__restrict__ tasks, const GemmPair *__restrict__ pairs) {
+    const GemmTile tile = tiles[blockIdx.x];
+    const GemmTask task = tasks[tile.task];
+    const int64_t col = (int64_t)tile.tn * THIN_ROWS + threadIdx.x;
+    if (col >= task.n) return;
+    const int m = task.m, n = task.n;
+    double acc[THIN_MAX];
+#pragma unroll
+    for (int i = 0; i < THIN_MAX; ++i) acc[i] = 0.0;
+    for (int p = task.pair_begin; p < task.pair_end; ++p) {
+        const GemmPair pr = pairs[p];
+        const double *a = A + pr.a_off;
+        const double *b = B + pr.b_off + col;
+        for (int kk = 0; kk < pr.k; ++kk) {
+            const double bv = b[(int64_t)kk * n];
+#pragma unroll
+            for (int i = 0; i < THIN_MAX; ++i)
+                if (i < m) acc[i] = fma(__ldg(a + (int64_t)i * pr.k + kk), bv, acc[i]);
+        }
+    }
+    double *c = C + task.c_off + col;
+#pragma unroll
+    for (int i = 0; i < THIN_MAX; ++i)
+        if (i < m) c[(int64_t)i * n] = acc[i];
+}
+
 // ---- host side: tiling of a task list --------------------------------------------------------------
 struct TileSet {
-    std::vector<GemmTile> tiles[3];  // 0: 128x128, 1: 64x64, 2: 32x32
+    std::vector<GemmTile> tiles[5];  // 0: 128x128, 1: 64x64, 2: 32x32 (tensor core); 3: thin n, 4: thin m (streaming)
 };
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -246,7 +315,7 @@ static void build_tiles(const std::vector<GemmTask> &tasks, const std::vector<Ge
         int64_t work;
         GemmTile tile;
     };
-    std::vector<Key> keyed[3];
+    std::vector<Key> keyed[5];
     static const int force_cfg = getenv("B200_GEMM_FORCE_CFG") ? atoi(getenv("B200_GEMM_FORCE_CFG")) : -1;
     for (size_t ti = 0; ti < tasks.size(); ++ti) {
         const GemmTask &tk = tasks[ti];
@@ -264,6 +333,21 @@ static void build_tiles(const std::vector<GemmTask> &tasks, const std::vector<Ge
         int cfg = 1;
         if (area32 * 10 < area64 * 7) cfg = 2;
         if (force_cfg >= 0) cfg = force_cfg;   // tuning knob (environment B200_GEMM_FORCE_CFG)
+        // thin products (one side <= THIN_MAX, short k-sum, long other side): streaming kernels
+        if (force_cfg < 0 && ksum <= THIN_KSUM) {
+            if (tk.n <= THIN_MAX && tk.m >= 4 * tk.n) cfg = 3;
+            else if (tk.m <= THIN_MAX && tk.n >= 4 * tk.m) cfg = 4;
+        }
+        if (cfg >= 3) {
+            int64_t nt = cdiv(cfg == 3 ? tk.m : tk.n, THIN_ROWS);
+            for (int64_t i = 0; i < nt; ++i) {
+                Key k;
+                k.work = ksum;
+                k.tile = cfg == 3 ? GemmTile{(int32_t)ti, (int32_t)i, 0, 0} : GemmTile{(int32_t)ti, 0, (int32_t)i, 0};
+                keyed[cfg].push_back(k);
+            }
+            continue;
+        }
         int b = cfg == 0 ? 128 : (cfg == 1 ? 64 : 32);
         for (int tm = 0; tm < cdiv(tk.m, b); ++tm)
             for (int tn = 0; tn < cdiv(tk.n, b); ++tn) {
@@ -273,7 +357,7 @@ static void build_tiles(const std::vector<GemmTask> &tasks, const std::vector<Ge
                 keyed[cfg].push_back(k);
             }
     }
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 5; ++c) {
         std::stable_sort(keyed[c].begin(), keyed[c].end(), [](const Key &x, const Key &y) { return x.work > y.work; });
         ts.tiles[c].clear();
         for (auto &k : keyed[c]) ts.tiles[c].push_back(k.tile);
@@ -283,18 +367,19 @@ static void build_tiles(const std::vector<GemmTask> &tasks, const std::vector<Ge
 struct DeviceGemmDesc {
     GemmTask *tasks = nullptr;
     GemmPair *pairs = nullptr;
-    GemmTile *tiles[3] = {nullptr, nullptr, nullptr};
-    int n_tiles[3] = {0, 0, 0};
+    GemmTile *tiles[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_tiles[5] = {0, 0, 0, 0, 0};
     bool vec = false;
     int device = -1;
     void release() {
         if (tasks) cudaFree(tasks);
         if (pairs) cudaFree(pairs);
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 5; ++c) {
             if (tiles[c]) cudaFree(tiles[c]);
+            tiles[c] = nullptr;
+        }
         tasks = nullptr;
         pairs = nullptr;
-        tiles[0] = tiles[1] = tiles[2] = nullptr;
     }
 };
 
@@ -310,7 +395,7 @@ static int upload_desc(const std::vector<GemmTask> &tasks, const std::vector<Gem
         B200_CUDA_CHECK(cudaMalloc(&d.pairs, pairs.size() * sizeof(GemmPair)));
         B200_CUDA_CHECK(cudaMemcpy(d.pairs, pairs.data(), pairs.size() * sizeof(GemmPair), cudaMemcpyHostToDevice));
     }
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 5; ++c) {
         d.n_tiles[c] = (int)ts.tiles[c].size();
         if (d.n_tiles[c]) {
             B200_CUDA_CHECK(cudaMalloc(&d.tiles[c], ts.tiles[c].size() * sizeof(GemmTile)));
@@ -345,6 +430,14 @@ static int launch_cfg(const DeviceGemmDesc &d, int cfg, const double *A, const d
 
 static int run_desc(const DeviceGemmDesc &d, const double *A, const double *B, double *C, cudaStream_t st) {
     int rc;
+    if (d.n_tiles[3]) {
+        thin_n_kernel<<<d.n_tiles[3], THIN_ROWS, 0, st>>>(A, B, C, d.tiles[3], d.tasks, d.pairs);
+        B200_CHECK_LAUNCH();
+    }
+    if (d.n_tiles[4]) {
+        thin_m_kernel<<<d.n_tiles[4], THIN_ROWS, 0, st>>>(A, B, C, d.tiles[4], d.tasks, d.pairs);
+        B200_CHECK_LAUNCH();
+    }
     if (d.vec && (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0) {
         if ((rc = launch_cfg<128, 128, 2, 4, true>(d, 0, A, B, C, st))) return rc;
         if ((rc = launch_cfg<64, 64, 2, 2, true>(d, 1, A, B, C, st))) return rc;
@@ -587,8 +680,8 @@ extern "C" int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m, const in
     build_tiles(tasks, pairs, ts);
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t b_tasks = al(tasks.size() * sizeof(GemmTask)), b_pairs = al(pairs.size() * sizeof(GemmPair));
-    size_t b_tiles[3], total = b_tasks + b_pairs;
-    for (int c = 0; c < 3; ++c) {
+    size_t b_tiles[5], total = b_tasks + b_pairs;
+    for (int c = 0; c < 5; ++c) {
         b_tiles[c] = al(ts.tiles[c].size() * sizeof(GemmTile));
         total += b_tiles[c];
     }
@@ -610,7 +703,7 @@ extern "C" int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m, const in
     d.pairs = reinterpret_cast<GemmPair *>(at);
     B200_CUDA_CHECK(cudaMemcpyAsync(at, pairs.data(), pairs.size() * sizeof(GemmPair), cudaMemcpyHostToDevice, st));
     at += b_pairs;
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 5; ++c) {
         d.n_tiles[c] = (int)ts.tiles[c].size();
         d.tiles[c] = reinterpret_cast<GemmTile *>(at);
         if (d.n_tiles[c])

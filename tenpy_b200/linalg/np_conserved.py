@@ -1081,7 +1081,7 @@ def _prepare_contraction(a, b, axes):
     return a, b, n
 
 
-def tensordot(a, b, axes=2, _out=None):
+def tensordot(a, b, axes=2, _out=None, _oz_slices=None):
     """Contract legs of `a` with legs of `b`, like ``np.tensordot`` (reference npc:3612).
 
     The block products of the whole contraction run as ONE grouped FP64 tensor-core GEMM launch per tile
@@ -1127,9 +1127,58 @@ def tensordot(a, b, axes=2, _out=None):
         buf = _out
     else:
         buf = backend.zeros(lay_c.size) if lay_c.has_padding else backend.empty(lay_c.size)
-    plan.run(a._buf, b._buf, buf)
+    if not (OZAKI['enabled'] and _tensordot_int8(a, b, plan, buf, _oz_slices)):
+        plan.run(a._buf, b._buf, buf)
     res._set_blocks(lay_c, buf)
     return res
+
+
+# Large dense block products run on the int8 tensor path (tcgen05, csrc/ozaki.cu): FP64 operands are cut into signed
+# 7-bit digit planes, the slice products are exact integer tensor-core GEMMs, the result is summed in FP64.  `slices`:
+# 8 = FP64 rounding level (error ~1e-15 (|A||B|)_ij), 7 (~1e-14) inside the Lanczos matvec (TwoSiteH passes
+# `_oz_slices`).  `min_flops` / `min_dim`: below, the DMMA grouped GEMM is as fast and needs no splitting pass.
+OZAKI = {'enabled': True, 'slices': 8, 'slices_matvec': 7, 'min_flops': 2.e9, 'min_dim': 256, 'calls': 0}
+
+
+def _oz_split_operand(lib, arr, role, rows, k, off, slices):
+    """int8 digit planes of one operand block (rows x k; role 'A': row-major rows x k, role 'B': row-major k x rows);
+    cached on Arrays their owner declared constant (``arr._oz_const = True``: the environments of a bond, which every
+    Lanczos iteration multiplies again)."""
+    cache = None
+    if getattr(arr, '_oz_const', False):
+        cache = arr.__dict__.setdefault('_oz_cache', {})
+        key = (role, slices, int(off), arr._buf.data_ptr())
+        hit = cache.get(key)
+        if hit is not None:
+            return hit
+    X = arr._buf[off:]
+    sp = lib.ozaki_split(rows, k, X, k, 1, slices) if role == 'A' else lib.ozaki_split(rows, k, X, 1, rows, slices)
+    if cache is not None:
+        cache[key] = sp
+    return sp
+
+
+def _tensordot_int8(a, b, plan, buf, slices=None):
+    """run a single large block product of a contraction plan on the int8 tensor path; False if not applicable"""
+    if plan.n_c != 1 or plan.n_pairs != 1:
+        return False
+    lib = backend.get_lib()
+    if not hasattr(lib, 'ozaki_mm'):
+        return False
+    m, n = int(plan.c_rows[0]), int(plan.c_cols[0])
+    geom = getattr(plan, '_oz_geom', None)
+    if geom is None:
+        _, a_off, b_off, kk = plan.pairs()
+        geom = plan._oz_geom = (int(a_off[0]), int(b_off[0]), int(kk[0]))
+    a_off, b_off, k = geom
+    if 2. * m * n * k < OZAKI['min_flops'] or min(m, n, k) < OZAKI['min_dim'] or k > 100000:
+        return False
+    s = int(slices or OZAKI['slices'])
+    a_s = _oz_split_operand(lib, a, 'A', m, k, a_off, s)
+    b_s = _oz_split_operand(lib, b, 'B', n, k, b_off, s)
+    lib.ozaki_mm(m, n, k, s, a_s, b_s, buf[int(plan.c_off[0]):], n)
+    OZAKI['calls'] += 1
+    return True
 
 
 def _is_identity_move(rec):

@@ -40,6 +40,40 @@ class _FakePlan:
             c[self.c_off[t]:self.c_off[t] + m * n] = acc.reshape(-1)
 
 
+class _FakeSplit:
+    """signed 7-bit digit planes of a (rows x k) matrix with row-wise power-of-two scaling, as oz_split_kernel makes them"""
+
+    def __init__(self, mat, slices):
+        mx = np.max(np.abs(mat), axis=1) if mat.size else np.zeros(mat.shape[0])
+        e = np.where(mx > 0, np.frexp(mx)[1], 0)
+        self.scale = np.ldexp(1.0, e)
+        v = mat / self.scale[:, None] * 64.0
+        digs = []
+        for _ in range(slices):
+            d = np.rint(v)
+            v = (v - d) * 128.0
+            digs.append(d.astype(np.int64))
+        self.digits = np.array(digs)
+
+    def data_ptr(self):
+        return id(self)
+
+
+def ozaki_product(a, b):
+    """A . B^T from two `_FakeSplit` operands (rows of b = columns of the product)"""
+    slices = a.digits.shape[0]
+    C = np.zeros((a.digits.shape[1], b.digits.shape[1]))
+    for g in range((slices + 3) // 4 - 1, -1, -1):
+        d_lo, d_hi = 4 * g, min(4 * g + 3, slices - 1)
+        h = None
+        for d in range(d_hi, d_lo - 1, -1):
+            Cd = sum(a.digits[t] @ b.digits[d - t].T for t in range(d + 1))
+            assert np.abs(Cd).max(initial=0) < 2**31
+            h = Cd.astype(np.float64) if h is None else h * 2.0**-7 + Cd
+        C += h * 2.0**(-12 - 7 * d_lo) * a.scale[:, None] * b.scale[None, :]
+    return C
+
+
 class FakeDeviceLib:
     name = 'FAKE numpy test double (tests only)'
 
@@ -157,6 +191,31 @@ class FakeDeviceLib:
             OUT1.numpy()[:outer * N1 * inner] = res[:, :N1].reshape(-1)
         if N2:
             OUT2.numpy()[:outer * N2 * inner] = res[:, N1:].reshape(-1)
+
+    # -- FP64 products on the int8 tensor path: numpy emulation of the scheme of csrc/ozaki.cu (same digits, exact integer
+    #    slice products, diagonals summed in FP64 from the least significant pass)
+    def ozaki_split(self, rows, k, X, ld_row, ld_k, slices):
+        self._count('ozaki_split')
+        x = X.numpy()
+        if ld_k == 1:
+            mat = np.lib.stride_tricks.as_strided(x, (rows, k), (8 * ld_row, 8)).copy()
+        else:
+            assert ld_row == 1
+            mat = np.lib.stride_tricks.as_strided(x, (rows, k), (8, 8 * ld_k)).copy()
+        return _FakeSplit(mat, slices)
+
+    def ozaki_mm(self, m, n, k, slices, a_split, b_split, C, ldc, accumulate=False):
+        self._count('ozaki_mm')
+        assert a_split.digits.shape == (slices, m, k) and b_split.digits.shape == (slices, n, k)
+        res = ozaki_product(a_split, b_split)
+        c = np.lib.stride_tricks.as_strided(C.numpy(), (m, n), (8 * ldc, 8))
+        if accumulate:
+            c += res
+        else:
+            c[...] = res
+
+    def ozaki_check_abort(self):
+        pass
 
     deflation = True
     deflation_tol = 0.

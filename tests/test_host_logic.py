@@ -447,7 +447,7 @@ def test_matvec_identity_env(fake_device):
         for i0 in range(psi.L - 1):
             Hc = TwoSiteH(eng.env, i0, combine=True, matvec_order='combined')
             Hi = TwoSiteH(eng.env, i0, combine=True, matvec_order='split')
-            Hi.identity_env = True
+            Hi.identity_env, Hi.mpo_apply = True, 'tensordot'      # the tensordot route (the fused kernel is tested below)
             theta = Hc.combine_theta(psi.get_theta(i0, 2))
             a, b = Hc.matvec(theta), Hi.matvec(theta)
             if mixer is None and Hi._id_env:      # no charges: the two components of t2 are shared views, nothing is gathered
