@@ -223,10 +223,10 @@ int b200_col_sqnorms_f64(int64_t rows, int64_t cols, int64_t ld, const double *X
  * replaces _svd_worker npc:4950 -> svd_robust.svd svd_robust.py:37 (LAPACK gesdd / gesvd). */
 /* switch the deflation of negligible directions in b200_block_svd_f64 on (default) / off; returns the old value */
 int b200_svd_set_deflation(int on);
-/* pivot eigen-solver of the Jacobi rounds: 1 = jacobi_eig_kernel (default), 2 = jacobi_eig_kernel_v2 (two barriers per
- * rotation set, csrc/jacobi_eig_core.cuh; host-verified, to be timed on the GPU in round 2); returns the old value */
+/* pivot eigen-solver of the Jacobi rounds: 1 = jacobi_eig_kernel (G in shared memory, three barriers per rotation set),
+ * 3 = jacobi_eig_kernel_v3 (G and Q in registers, warp shuffles, two barriers per set); returns the old value */
 int b200_svd_set_eig_variant(int variant);
-/* inner sweeps of the version-2 pivot eigen-solver (1..16, default 4): profiles/jacobi_sweeps_study.md finds the number
+/* inner sweeps of the version-3 pivot eigen-solver (1..16, default 2): profiles/jacobi_sweeps_study.md finds the number
  * of outer sweeps unchanged between 2 and 4; returns the old value */
 int b200_svd_set_eig_inner_sweeps(int n);
 /* additional deflation threshold relative to |A_i|_F (default 0 = rounding level only): directions with a

@@ -22,16 +22,7 @@ def get_lib():
     lib = _state['lib']
     if lib is None:
         lib = _state['lib'] = DeviceLib()
-        _apply_optins(lib)
     return lib
-
-
-def _apply_optins(lib):
-    """B200_OPTINS (tenpy_b200/optins.py): opt-in kernels for a whole process"""
-    import os
-    if os.environ.get('B200_OPTINS', '').strip():
-        from . import optins
-        optins.apply(lib=lib)
 
 
 def use_library(lib):
@@ -47,7 +38,6 @@ def use_library(lib):
     npc = sys.modules.get('tenpy_b200.linalg.np_conserved')
     if npc is not None:
         npc._PLAN_CACHE.clear()
-    _apply_optins(lib)
     return lib
 
 

@@ -152,6 +152,7 @@ struct OzGemmArgs {
     int32_t nstages;
     int32_t accumulate;          // 0: C = A.B, 1: C += A.B
     int32_t *abort_flag;
+    long long *dbg;              // optional (B200_OZ_DEBUG): cycle counters of CTA 0, see b200_ozaki_mm_f64
 };
 
 constexpr int OZ_THREADS = 256;
@@ -195,13 +196,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         // ================= producer: bulk copies of slice tiles =================
         uint32_t it = 0;
         bool ok = true;
+        long long t_wait = 0, t0 = clock64();
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             const int mt = tile % mt_count, nt = tile / mt_count;
             for (int g = npass - 1; g >= 0 && ok; --g) {
                 const int nsl = min(s, 4 * g + 4);                   // slices 0 .. nsl-1 of both operands are needed
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int slot = it % nst;
+                    const long long tw = clock64();
                     ok = mbar_wait(&empty_bar[slot], ((it / nst) & 1) ^ 1, p.abort_flag);
+                    t_wait += clock64() - tw;
                     if (!ok) break;
                     mbar_expect_tx(&full_bar[slot], 2u * nsl * tile_bytes);
                     uint8_t *st = oz_smem + (size_t)slot * stage_bytes;
@@ -214,35 +218,43 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                 }
             }
         }
+        if (p.dbg && blockIdx.x == 0) {
+            p.dbg[0] = clock64() - t0;
+            p.dbg[1] = t_wait;
+        }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
         const uint32_t idesc = idesc_s8(OZ_TILE, OZ_TILE);
         uint32_t it = 0, pass_it = 0;
         bool ok = true;
+        long long t_full = 0, t_acc = 0, t0 = clock64();
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
                 const int d_lo = 4 * g, d_hi = min(4 * g + 3, s - 1);
-                const int nsl = d_hi + 1;
+                long long tw = clock64();
                 ok = mbar_wait(&acc_empty, (pass_it & 1) ^ 1, p.abort_flag);   // epilogue has drained the accumulators
+                t_acc += clock64() - tw;
                 if (!ok) break;
                 fence_after_sync();
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int slot = it % nst;
+                    tw = clock64();
                     ok = mbar_wait(&full_bar[slot], (it / nst) & 1, p.abort_flag);
+                    t_full += clock64() - tw;
                     if (!ok) break;
                     fence_after_sync();
+                    // descriptors of slice tile 0 of A and B in this slot; the other tiles / k-steps differ only in the
+                    // start-address field (bytes >> 4, low bits of the descriptor): one 64-bit add per MMA operand
                     const uint32_t sa = smem_addr(oz_smem + (size_t)slot * stage_bytes);
-                    const uint32_t sb = sa + (uint32_t)s * tile_bytes;
+                    const uint64_t da0 = oz_desc(sa), db0 = oz_desc(sa + (uint32_t)s * tile_bytes);
+                    const uint32_t tile16 = tile_bytes >> 4, kstep16 = (2u * OZ_CHUNK_BYTES) >> 4;
                     for (int d = d_lo; d <= d_hi; ++d) {
                         const uint32_t acc = tmem + (uint32_t)(d - d_lo) * OZ_TILE;
-                        const int t0 = max(0, d - (nsl - 1)), t1 = min(d, nsl - 1);
-                        for (int t = t0; t <= t1; ++t) {
-                            const int u = d - t;
-                            for (int kk = 0; kk < cps / 2; ++kk) {
-                                const uint32_t off = (uint32_t)kk * 2u * OZ_CHUNK_BYTES;
-                                mma_i8(acc, oz_desc(sa + t * tile_bytes + off), oz_desc(sb + u * tile_bytes + off), idesc,
-                                       (ks | (t - t0) | kk) ? 1u : 0u);
-                            }
+                        for (int t = 0; t <= d; ++t) {                 // all pairs (t, u = d - t) of the diagonal
+                            const uint64_t ad = da0 + (uint64_t)((uint32_t)t * tile16);
+                            const uint64_t bd = db0 + (uint64_t)((uint32_t)(d - t) * tile16);
+                            mma_i8(acc, ad, bd, idesc, (ks | t) ? 1u : 0u);
+                            if (cps == 4) mma_i8(acc, ad + kstep16, bd + kstep16, idesc, 1u);
                         }
                     }
                     mma_commit(&empty_bar[slot]);                      // slot free once these MMAs have read it
@@ -250,25 +262,32 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                 if (ok) mma_commit(&acc_full);                         // accumulators of this pass complete
             }
         }
+        if (p.dbg && blockIdx.x == 0) {
+            p.dbg[2] = clock64() - t0;
+            p.dbg[3] = t_full;
+            p.dbg[4] = t_acc;
+        }
     } else if (warp >= 4) {
         // ================= epilogue: TMEM -> FP64 -> C =================
         const int q = warp - 4;                                        // TMEM lane quarter = warp id % 4
         uint32_t pass_it = 0;
         bool ok = true;
+        long long t_wait = 0, t0 = clock64();
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             const int mt = tile % mt_count, nt = tile / mt_count;
-            const int row = mt * OZ_TILE + q * 32 + lane;
-            const double sa = p.sA[row];                               // scales are padded to whole tiles
-            double *crow = p.C + (int64_t)row * p.ldc + (int64_t)nt * OZ_TILE;
             const double *sbp = p.sB + (int64_t)nt * OZ_TILE;
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
                 const int d_lo = 4 * g, d_hi = min(4 * g + 3, s - 1);
+                const long long tw = clock64();
                 ok = mbar_wait(&acc_full, pass_it & 1, p.abort_flag);
+                t_wait += clock64() - tw;
                 if (!ok) break;
                 fence_after_sync();
                 // weight of the pass: 2^(-12 - 7 d_lo)
-                const double w = __longlong_as_double((long long)(1023 - 12 - 7 * d_lo) << 52) * sa;
+                const double wpass = __longlong_as_double((long long)(1023 - 12 - 7 * d_lo) << 52);
                 const bool add = (g != npass - 1) || p.accumulate;
+                const int row0 = mt * OZ_TILE + q * 32;                // the 32 rows of this warp
+                const double sa_l = p.sA[row0 + lane];                 // scale of this lane's row (sA is padded to whole tiles)
                 for (int c0 = 0; c0 < OZ_TILE; c0 += 32) {
                     double h[32];
                     uint32_t r[32];
@@ -285,21 +304,48 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                             h[j] = fma(h[j], 0.0078125,
                                        __hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0);
                     }
-                    if (row < p.M) {
-                        const int ncol = min(32, p.N - (nt * OZ_TILE + c0));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) h[j] *= sa_l;          // row scale 2^ea_i while lane = row
+                    // lane = row, register = column  ->  lane = column, register = row (butterfly transposition with
+                    // static register indices), so that every global access of the warp is one contiguous 256-byte row
+                    // segment of C instead of 32 scattered 8-byte words
+#pragma unroll
+                    for (int b = 16; b >= 1; b >>= 1) {
+                        const bool up = (lane & b) != 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            if (j < ncol) {
-                                double v = h[j] * w * sbp[c0 + j];
-                                if (add) v += crow[c0 + j];
-                                crow[c0 + j] = v;
+                            if ((j & b) == 0) {
+                                const double give = up ? h[j] : h[j | b];
+                                const double got = __shfl_xor_sync(0xffffffffu, give, b);
+                                if (up) h[j] = got; else h[j | b] = got;
                             }
+                        }
+                    }
+                    const int col = nt * OZ_TILE + c0 + lane;
+                    const double wsb = wpass * sbp[c0 + lane];         // sB is padded to whole tiles
+                    double *cp = p.C + (int64_t)row0 * p.ldc + col;
+                    if (col < p.N) {
+                        if (add) {
+                            double old[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) old[j] = (row0 + j < p.M) ? cp[(int64_t)j * p.ldc] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (row0 + j < p.M) cp[(int64_t)j * p.ldc] = fma(h[j], wsb, old[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (row0 + j < p.M) cp[(int64_t)j * p.ldc] = h[j] * wsb;
                         }
                     }
                 }
                 fence_before_sync();
                 mbar_arrive(&acc_empty);
             }
+        }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
+            p.dbg[5] = clock64() - t0;
+            p.dbg[6] = t_wait;
         }
     }
     fence_before_sync();
@@ -391,6 +437,14 @@ extern "C" int b200_ozaki_mm_f64(int64_t m, int64_t n, int64_t k, int32_t slices
     p.slices = slices;
     p.accumulate = accumulate ? 1 : 0;
     p.abort_flag = g_abort_flag;
+    p.dbg = nullptr;
+    static const bool debug = getenv("B200_OZ_DEBUG") != nullptr;   // cycle counters of CTA 0 -> stderr (synchronises)
+    long long *dbg_dev = nullptr;
+    if (debug) {
+        B200_CUDA_CHECK(cudaMalloc(&dbg_dev, 8 * sizeof(long long)));
+        B200_CUDA_CHECK(cudaMemset(dbg_dev, 0, 8 * sizeof(long long)));
+        p.dbg = dbg_dev;
+    }
     // pipeline shape: as many k chunks per stage as leave at least two stages in shared memory
     static const int force_cps = getenv("B200_OZ_CPS") ? atoi(getenv("B200_OZ_CPS")) : 0;   // tuning knob (2 or 4)
     p.cps = force_cps == 2 ? 2 : 4;
@@ -411,6 +465,14 @@ extern "C" int b200_ozaki_mm_f64(int64_t m, int64_t n, int64_t k, int32_t slices
     int grid = (int)std::min<int64_t>(ntiles, sm_count());
     oz_gemm_kernel<<<grid, OZ_THREADS, smem, (cudaStream_t)stream>>>(p);
     B200_CHECK_LAUNCH();
+    if (debug) {
+        long long h[8];
+        B200_CUDA_CHECK(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(dbg_dev);
+        fprintf(stderr, "[oz_gemm m=%lld n=%lld k=%lld s=%d cps=%d stages=%d] CTA0 cycles: producer total %lld wait_empty %lld | "
+                "mma total %lld wait_full %lld wait_acc_empty %lld | epilogue total %lld wait_acc_full %lld\n",
+                (long long)m, (long long)n, (long long)k, slices, p.cps, p.nstages, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+    }
     return B200_OK;
 }
 

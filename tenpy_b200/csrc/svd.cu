@@ -23,7 +23,6 @@
 #include <vector>
 
 #include "common.cuh"
-#include "jacobi_eig_core.cuh"
 
 namespace b200 {
 
@@ -346,103 +345,150 @@ __global__ void __launch_bounds__(JTHREADS)
     if (tid == 0) flags[blockIdx.x] = 1;
 }
 
-// Version 2 of the pivot eigen-solver (see jacobi_eig_core.cuh): the 16 disjoint rotations of a set are applied from
-// both sides in one pass over a double-buffered G -> two barriers per set instead of three, no in-place hazards.  Same
-// interface, same rotations (to rounding) as jacobi_eig_kernel; selected at run time by b200_svd_set_eig_variant(2).
-// The phase functions are the ones tests/csrc/eig_core_host.cpp checks on the CPU.
+// Version 3 of the pivot eigen-solver: G and Q live in REGISTERS, rotations go through warp shuffles, shared memory is
+// only the transposition buffer -> two barriers per rotation set and no dependent shared-memory read-modify-write chains
+// (version 1: three barriers and three shared-memory passes per set, 100-116 us per round on the B200 = the latency floor
+// of the whole block SVD, profiles/r01d_launch_shares.md).
+//   thread (warp w, lane l) holds G[l][4w+i] and Q[4w+i][l], i < 4 (256 threads).
+//   one rotation set (16 disjoint pairs (p, q), the same round-robin order as version 1):
+//     1. every lane computes the rotation of the pair its row index l belongs to from sA (= the current G in shared
+//        memory: G[p][p], G[q][q], G[p][q]); the 8 warps do this redundantly instead of waiting for one another;
+//     2. rows:    G' = J G        lane l combines its value with lane partner(l)'s (shuffle);
+//     3. columns: G'' = G' J^T    = (J G'^T)^T and G'' is symmetric: write G' to sT, barrier, read it TRANSPOSED and
+//        apply the same row rotation again -- the result is G''[l][c] in the thread that holds G[l][c];
+//     4. Q <- Q J^T (columns p, q of every row: lanes p, q of the same warp, shuffle);
+//     5. write G'' to sA for the parameters of the next set, barrier.
+// Same interface and the same rotations (to rounding) as version 1.
+__device__ __forceinline__ int jeig3_partner(int x, int step) {
+    // round-robin tournament over JP = 32 indices, index 31 fixed: pairs (31, step) and ((step+j) % 31, (step-j) % 31)
+    if (x == JP - 1) return step;
+    int j = x - step;
+    if (j < 0) j += JP - 1;
+    if (j == 0) return JP - 1;
+    int y = (j <= JB - 1) ? step - j : step + (JP - 1 - j);
+    if (y < 0) y += JP - 1;
+    if (y >= JP - 1) y -= JP - 1;
+    return y;
+}
+
 __global__ void __launch_bounds__(JTHREADS)
-    jacobi_eig_kernel_v2(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
+    jacobi_eig_kernel_v3(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
                          const int *__restrict__ done, double tol_scale, const double *__restrict__ Gbuf, int nsplit,
                          double *__restrict__ QTbuf, int *__restrict__ flags, int inner_sweeps) {
-    static_assert(jeig::N == JP && jeig::LD == JLDG, "pivot order / smem stride of jacobi_eig_core.cuh");
-    __shared__ double sGa[JP * JLDG], sGb[JP * JLDG];
-    __shared__ double sQa[JP * JLDG], sQb[JP * JLDG];
-    __shared__ double s_alpha[JP], s_beta[JP];
-    __shared__ int s_partner[JP];
+    __shared__ double sA[JP * JLDG];
+    __shared__ double sT[JP * JLDG];
     __shared__ double red[32];
+    __shared__ int s_rank[JP];
+    __shared__ int s_any;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) flags[blockIdx.x] = 0;
     const int mi = cta_mat[blockIdx.x];
     if (done[mi]) return;
     const JMat mt = mats[mi];
     if (2 * (blockIdx.x - mt.cta_begin) >= mt.nb_act) return;
+    double g[4], qv[4];
     {
         const int nch = (mt.ldy + JKC - 1) / JKC;
         const int ns = nsplit < nch ? nsplit : nch;
         const double *G = Gbuf + (int64_t)blockIdx.x * nsplit * (JP * JP);
-        for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = 4 * warp + i;
             double v = 0.0;
-            for (int sp = 0; sp < ns; ++sp) v += G[sp * (JP * JP) + idx];
-            sGa[(idx / JP) * JLDG + (idx % JP)] = v;
+            for (int sp = 0; sp < ns; ++sp) v += G[sp * (JP * JP) + c * JP + lane];   // G[c][l] = G[l][c], coalesced
+            g[i] = v;
+            sA[lane * JLDG + c] = v;
+            qv[i] = (c == lane) ? 1.0 : 0.0;
         }
     }
+    if (tid == 0) s_any = 0;
     __syncthreads();
     // ---- convergence measure of this pair (as version 1) ----
     const double defl2 = mt.defl * mt.defl;
     double offmax = 0.0;
-    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
-        int r = idx / JP, c = idx % JP;
-        if (r < c) {
-            const double drr = sGa[r * JLDG + r], dcc = sGa[c * JLDG + c];
-            if (drr > defl2 && dcc > defl2) offmax = fmax(offmax, fabs(sGa[r * JLDG + c]) / sqrt(drr * dcc));
+    {
+        const double dl = sA[lane * JLDG + lane];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = 4 * warp + i;
+            const double dc = sA[c * JLDG + c];
+            if (lane < c && dl > defl2 && dc > defl2) offmax = fmax(offmax, fabs(g[i]) / sqrt(dl * dc));
         }
     }
     offmax = warp_max(offmax);
     if (lane == 0) red[warp] = offmax;
     __syncthreads();
-    if (tid == 0) {
-        double v = 0.0;
-        for (int w = 0; w < JTHREADS / 32; ++w) v = fmax(v, red[w]);
-        red[0] = v;
-    }
-    __syncthreads();
-    offmax = red[0];
+    offmax = 0.0;
+#pragma unroll
+    for (int w = 0; w < JTHREADS / 32; ++w) offmax = fmax(offmax, red[w]);
     const double tol = tol_scale * sqrt((double)mt.p);
     if (!(offmax > tol)) return;  // uniform for the whole CTA
     if (tid == 0) atomicAdd(&rot_count[mi], 1);
 
-    // ---- G = Q L Q^T: barrier-separated phases on double buffers ----
-    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
-        int r = idx / JP, c = idx % JP;
-        sQa[r * JLDG + c] = (r == c) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    double *Gc = sGa, *Gn = sGb, *Qc = sQa, *Qn = sQb;
     const double tol_in = 1e-15;
     for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
-        int any = 0;
         for (int step = 0; step < JP - 1; ++step) {
-            if (tid < jeig::NPAIR) any |= jeig::phase_params(tid, step, Gc, defl2, tol_in, s_partner, s_alpha, s_beta);
+            // 1. rotation of the pair that contains row index `lane`
+            const int partner = jeig3_partner(lane, step);
+            const bool is_p = lane < partner;
+            const int p = is_p ? lane : partner, q = is_p ? partner : lane;
+            const double gpp = sA[p * JLDG + p], gqq = sA[q * JLDG + q], gpq = sA[p * JLDG + q];
+            double c = 1.0, sn = 0.0;
+            if (fabs(gpq) > tol_in * sqrt(fabs(gpp * gqq)) && gpp > defl2 && gqq > defl2) {
+                const double aa = gqq - gpp, bb = 2.0 * gpq;
+                const double hh = sqrt(aa * aa + bb * bb);
+                const double tt = (aa >= 0.0) ? bb / (aa + hh) : bb / (aa - hh);
+                c = rsqrt(1.0 + tt * tt);
+                sn = tt * c;
+                if (warp == 0) s_any = 1;     // benign race: every writer stores 1
+            }
+            // row p: c x_p - s x_q ;  row q: s x_p + c x_q   -> as "own * c + other * (-s | +s)"
+            const double so = is_p ? -sn : sn;
+            // 2. rows of G
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double y = __shfl_sync(0xffffffffu, g[i], partner);
+                g[i] = fma(so, y, c * g[i]);
+                sT[lane * JLDG + 4 * warp + i] = g[i];
+            }
+            // 4. columns of Q (independent of the barrier below)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double y = __shfl_sync(0xffffffffu, qv[i], partner);
+                qv[i] = fma(so, y, c * qv[i]);
+            }
             __syncthreads();
-            for (int e = tid; e < JP * JP; e += JTHREADS)
-                jeig::phase_apply_elem(e, Gc, Gn, Qc, Qn, s_partner, s_alpha, s_beta);
+            // 3. columns of G through the transposed read
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double t = sT[(4 * warp + i) * JLDG + lane];
+                const double y = __shfl_sync(0xffffffffu, t, partner);
+                g[i] = fma(so, y, c * t);
+                sA[lane * JLDG + 4 * warp + i] = g[i];
+            }
             __syncthreads();
-            double *t1 = Gc;
-            Gc = Gn;
-            Gn = t1;
-            double *t2 = Qc;
-            Qc = Qn;
-            Qn = t2;
         }
-        if (!__syncthreads_or(any)) break;
+        const int any = s_any;
+        __syncthreads();
+        if (!any) break;
+        if (tid == 0) s_any = 0;
+        __syncthreads();
     }
-    // order the new rows by descending eigenvalue; rank kept in the padding column of the current G buffer
+    // order the new rows by descending eigenvalue (norm^2): rank[i] = number of entries with larger diagonal (ties by index)
     if (tid < JP) {
-        double di = Gc[tid * JLDG + tid];
+        const double di = sA[tid * JLDG + tid];
         int rk = 0;
         for (int k = 0; k < JP; ++k) {
-            double dk = Gc[k * JLDG + k];
+            const double dk = sA[k * JLDG + k];
             if (dk > di || (dk == di && k < tid)) ++rk;
         }
-        Gc[tid * JLDG + JP] = (double)rk;
+        s_rank[tid] = rk;
     }
     __syncthreads();
     double *QT = QTbuf + (int64_t)blockIdx.x * (JP * JP);
-    for (int idx = tid; idx < JP * JP; idx += JTHREADS) {
-        int i = idx / JP, k = idx % JP;
-        int rk = (int)Gc[i * JLDG + JP];
-        QT[rk * JP + k] = Qc[k * JLDG + i];
-    }
+    // QT[rank[i]][k] = Q[k][i]; this thread holds Q[4w+j][lane]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) QT[s_rank[lane] * JP + 4 * warp + i] = qv[i];
     if (tid == 0) flags[blockIdx.x] = 1;
 }
 
@@ -609,8 +655,8 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- host driver -----------------------------------------------------------------------------------
-static int g_eig_variant = 1;   // pivot eigen-solver: 1 = jacobi_eig_kernel (GPU-verified), 2 = jacobi_eig_kernel_v2
-static int g_eig_inner_sweeps = J_INNER_SWEEPS;   // inner sweeps of version 2 (version 1: fixed J_INNER_SWEEPS)
+static int g_eig_variant = 1;   // pivot eigen-solver: 1 = jacobi_eig_kernel (shared memory), 3 = jacobi_eig_kernel_v3 (registers + shuffles)
+static int g_eig_inner_sweeps = J_INNER_SWEEPS;   // inner sweeps of version 3 (version 1: fixed J_INNER_SWEEPS)
 struct JLayout {
     std::vector<JMat> mats;
     std::vector<int> cta_mat;
@@ -749,8 +795,8 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
             jacobi_gram_kernel<<<dim3((unsigned)nsplit, (unsigned)n_cta), JTHREADS, jacobi_smem_bytes(), st>>>(
                 wf, d_mats, d_cta, d_rmap, round_counter, d_done, d_G);
             B200_CHECK_LAUNCH();
-            if (g_eig_variant == 2)
-                jacobi_eig_kernel_v2<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit,
+            if (g_eig_variant == 3)
+                jacobi_eig_kernel_v3<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit,
                                                                d_QT, d_flags, g_eig_inner_sweeps);
             else
                 jacobi_eig_kernel<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit, d_QT,
@@ -865,7 +911,7 @@ extern "C" double b200_svd_set_deflation_tol(double tol_rel) {
 }
 extern "C" int b200_svd_set_eig_variant(int variant) {
     int old = g_eig_variant;
-    if (variant == 1 || variant == 2) g_eig_variant = variant;
+    if (variant == 1 || variant == 3) g_eig_variant = variant;
     return old;
 }
 

@@ -19,7 +19,7 @@ Conventions (identical to the reference):
 
 import numpy as np
 
-__all__ = ['QTYPE', 'ChargeInfo', 'LegCharge', 'LegPipe']
+__all__ = ['QTYPE', 'ChargeInfo', 'DipolarChargeInfo', 'LegCharge', 'LegPipe']
 
 QTYPE = np.int64  # reference: charges.py:35
 
@@ -60,6 +60,15 @@ _find_row_differences = _row_change_points
 class ChargeInfo:
     """Meta-data of the conserved charges: how many, and their modulus (reference charges.py:39)."""
 
+    trivial_shift = True     # translations do not change the charges (reference charges.py:82; False only for dipoles)
+
+    def shift_charges(self, charges, dx):
+        """charges after a translation by `dx` sites: unchanged without dipole conservation (reference charges.py:309)"""
+        return charges
+
+    def shift_charges_horizontal(self, charges, dx):
+        return charges
+
     def __init__(self, mod=(), names=None):
         self._mod = np.array(mod, dtype=QTYPE).reshape(-1)
         self._qnumber = len(self._mod)
@@ -89,6 +98,28 @@ class ChargeInfo:
         """Concatenate several ChargeInfo (reference charges.py:170)."""
         mod = np.concatenate([c.mod for c in chinfos]) if len(chinfos) else []
         names = sum([c.names for c in chinfos], [])
+        return cls(mod, names)
+
+    def _charge_index(self, charge):
+        if isinstance(charge, str):
+            return self.names.index(charge)
+        return int(charge)
+
+    @classmethod
+    def drop(cls, chinfo, charge=None):
+        """`chinfo` without the given charge(s) (index / name / list; ``None`` drops all; reference charges.py:187)"""
+        if charge is None:
+            return cls()
+        drop = [chinfo._charge_index(c) for c in (charge if isinstance(charge, (list, tuple)) else [charge])]
+        keep = [i for i in range(chinfo.qnumber) if i not in drop]
+        return cls([chinfo.mod[i] for i in keep], [chinfo.names[i] for i in keep])
+
+    @classmethod
+    def change(cls, chinfo, charge, new_qmod, new_name=''):
+        """`chinfo` with another modulus for one charge (reference charges.py:215)"""
+        i = chinfo._charge_index(charge)
+        mod, names = list(chinfo.mod), list(chinfo.names)
+        mod[i], names[i] = new_qmod, new_name
         return cls(mod, names)
 
     def make_valid(self, charges=None):
@@ -133,6 +164,13 @@ class ChargeInfo:
         self._mask = self._mod != 1
         self._mod_masked = self._mod[self._mask]
         self.names = list(names)
+
+
+class DipolarChargeInfo(ChargeInfo):
+    """Charges with dipole conservation (reference charges.py:331) are not provided by the B200 engine."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError('DipolarChargeInfo is outside the scope of tenpy_b200')
 
 
 class LegCharge:
@@ -198,6 +236,35 @@ class LegCharge:
         res.sorted = res.is_sorted()
         res.bunched = res.is_bunched()
         return res
+
+    @classmethod
+    def from_add_charge(cls, legs, chargeinfo=None):
+        """several legs of equal length and qconj -> one leg carrying all their charges (reference charges.py:843)"""
+        legs = list(legs)
+        if chargeinfo is None:
+            chargeinfo = ChargeInfo.add([l.chinfo for l in legs])
+        if any(l.ind_len != legs[0].ind_len or l.qconj != legs[0].qconj for l in legs):
+            raise ValueError('legs to be combined need the same length and qconj')
+        return cls.from_qflat(chargeinfo, np.concatenate([l.to_qflat() for l in legs], axis=1), legs[0].qconj)
+
+    @classmethod
+    def from_drop_charge(cls, leg, charge=None, chargeinfo=None):
+        """`leg` without the given charge(s) (reference charges.py:875)"""
+        if chargeinfo is None:
+            chargeinfo = ChargeInfo.drop(leg.chinfo, charge)
+        if charge is None:
+            keep = []
+        else:
+            drop = [leg.chinfo._charge_index(c) for c in (charge if isinstance(charge, (list, tuple)) else [charge])]
+            keep = [i for i in range(leg.chinfo.qnumber) if i not in drop]
+        return cls.from_qflat(chargeinfo, leg.to_qflat()[:, keep], leg.qconj)
+
+    @classmethod
+    def from_change_charge(cls, leg, charge, new_qmod, new_name='', chargeinfo=None):
+        """`leg` with another modulus for one charge (reference charges.py:905)"""
+        if chargeinfo is None:
+            chargeinfo = ChargeInfo.change(leg.chinfo, charge, new_qmod, new_name)
+        return cls.from_qflat(chargeinfo, leg.to_qflat(), leg.qconj)
 
     @classmethod
     def from_qdict(cls, chargeinfo, qdict, qconj=1):

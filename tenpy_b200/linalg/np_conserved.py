@@ -87,6 +87,20 @@ def _allowed_qindices(legs, qtotal, chinfo):
     return qd
 
 
+class _WriteThroughBlock(np.ndarray):
+    """host copy of one stored block; assignments are copied to the device buffer (see :meth:`Array.get_block`)"""
+    _target = None
+
+    def __setitem__(self, key, value):
+        np.ndarray.__setitem__(self, key, value)
+        if self._target is not None:
+            buf, o, s = self._target
+            buf[o:o + s].copy_(backend.to_device(np.ascontiguousarray(np.asarray(self), dtype=np.float64).reshape(-1)))
+
+    def __array_finalize__(self, obj):
+        self._target = None           # views / results of arithmetic are plain host data
+
+
 class Array:
     r"""A block-sparse tensor with abelian charge conservation, stored in packed HBM (reference npc:154).
 
@@ -207,6 +221,8 @@ class Array:
     @classmethod
     def from_blocks(cls, legcharges, qdata, blocks, qtotal=None, labels=None):
         """Create from host blocks: `qdata` (n, rank) qindices, `blocks` list of ndarrays."""
+        if cls is Array and any(np.iscomplexobj(b) for b in blocks):
+            return ComplexArray.from_blocks(legcharges, qdata, blocks, qtotal, labels)
         res = cls(legcharges, np.float64, qtotal, labels)
         qdata = np.asarray(qdata, dtype=np.int64).reshape(-1, res.rank)
         layout, perm = BlockLayout.from_legs(res.legs, qdata)
@@ -235,6 +251,11 @@ class Array:
     @classmethod
     def from_ndarray_trivial(cls, data_flat, dtype=None, labels=None):
         """Array without charges from a dense ndarray (reference npc:420)."""
+        if np.iscomplexobj(data_flat) or (dtype is not None and np.dtype(dtype).kind == 'c'):
+            data_flat = np.asarray(data_flat)
+            chinfo = ChargeInfo()
+            return ComplexArray.from_ndarray(data_flat, [LegCharge.from_trivial(s, chinfo) for s in data_flat.shape],
+                                             labels=labels)
         data_flat = np.asarray(data_flat, dtype=np.float64)
         chinfo = ChargeInfo()
         legs = [LegCharge.from_trivial(s, chinfo) for s in data_flat.shape]
@@ -246,6 +267,9 @@ class Array:
         """Dense ndarray -> Array, keeping blocks with an entry ``> cutoff`` (reference npc:451)."""
         if cutoff is None:
             cutoff = 1e-16
+        if cls is Array and (np.iscomplexobj(data_flat) or (dtype is not None and np.dtype(dtype).kind == 'c')):
+            return ComplexArray.from_ndarray(data_flat, legcharges, dtype, qtotal, cutoff, labels, raise_wrong_sector,
+                                             warn_wrong_sector)
         data_flat = np.asarray(data_flat, dtype=np.float64)
         legcharges = list(legcharges)
         if data_flat.shape != tuple(l.ind_len for l in legcharges):
@@ -323,15 +347,34 @@ class Array:
         return res
 
     def get_block(self, qindices, insert=False, raise_incomp_q=False):
-        """Host copy of the block with given qindices, or None (reference npc:1330; read-only here)."""
+        """The block with given qindices as a host array, or None (reference npc:1330).  The reference hands out a view
+        of its host block; here the result is a host copy whose item assignments are written through to the device buffer
+        (``block[:] = values`` as in the reference's ``full_diag_effH``, dmrg.py:1209).  ``insert=True`` stores a zero
+        block first if there is none."""
         qindices = np.asarray(qindices, dtype=np.int64)
         lay = self._layout
         match = np.nonzero(np.all(lay.qdata == qindices, axis=1))[0]
         if len(match) == 0:
-            return None
+            if not insert:
+                return None
+            part = np.zeros(self.chinfo.qnumber, dtype=QTYPE)
+            for leg, qi in zip(self.legs, qindices):
+                part = part + leg.get_charge(int(qi)) * leg.qconj
+            if np.any(self.chinfo.make_valid(part) != self.qtotal):
+                if raise_incomp_q:
+                    raise ValueError('trying to get block for incompatible charges')
+                return None
+            shape = tuple(int(leg.get_block_sizes()[int(qi)]) for leg, qi in zip(self.legs, qindices))
+            new = Array.from_blocks(self.legs, np.concatenate([lay.qdata, qindices[None, :]], axis=0),
+                                    self.get_blocks_host() + [np.zeros(shape)], self.qtotal, self._labels)
+            self._layout, self._buf = new._layout, new._buf
+            lay = self._layout
+            match = np.nonzero(np.all(lay.qdata == qindices, axis=1))[0]
         i = int(match[0])
-        o, s = lay.offsets[i], lay.sizes[i]
-        return backend.to_host(self._buf[o:o + s]).reshape(lay.shapes[i])
+        o, s = int(lay.offsets[i]), int(lay.sizes[i])
+        host = backend.to_host(self._buf[o:o + s]).reshape(lay.shapes[i]).view(_WriteThroughBlock)
+        host._target = (self._buf, o, s)
+        return host
 
     # ------------------------------------------------------------------ labels
     def get_leg_index(self, label):
@@ -973,7 +1016,9 @@ def _union_layout(legs, a, b):
 # ====================================================================== module level functions
 def zeros(legcharges, dtype=np.float64, qtotal=None, labels=None):
     """Array without stored blocks (reference npc:3108)."""
-    return Array(legcharges, dtype, qtotal, labels)
+    if np.dtype(dtype).kind == 'c':
+        return ComplexArray(Array(legcharges, np.float64, qtotal, labels), Array(legcharges, np.float64, qtotal, labels))
+    return Array(legcharges, np.float64 if np.dtype(dtype).kind in 'fiub' else dtype, qtotal, labels)
 
 
 def ones(legcharges, dtype=np.float64, qtotal=None, labels=None):
@@ -1088,6 +1133,8 @@ def tensordot(a, b, axes=2, _out=None, _oz_slices=None):
     shape (worker: reference pyx:1498 / npc:4846).  ``_out`` (internal): device buffer of exactly the result's packed
     size without alignment padding, written instead of a fresh allocation (lets a caller place the result inside a
     larger packed buffer)."""
+    if isinstance(a, ComplexArray) or isinstance(b, ComplexArray):
+        return _sf.complex_tensordot(_sys.modules[__name__], a, b, axes)
     a, b, n = _prepare_contraction(a, b, axes)
     cut_a = a.rank - n
     if cut_a == 0 and b.rank == n:
@@ -1252,27 +1299,27 @@ def inner(a, b, axes='labels', do_conj=False):
         for la_, lb_ in zip(a.legs, b.legs):
             la_.test_equal(lb_)
         if np.any(a.qtotal != b.qtotal):
-            return 0.0
+            return np.float64(0.0)
     else:
         for la_, lb_ in zip(a.legs, b.legs):
             la_.test_contractible(lb_)
         if np.any(a.chinfo.make_valid(a.qtotal + b.qtotal) != 0):
-            return 0.0
+            return np.float64(0.0)
     la, lb = a._layout, b._layout
     if la.nblocks == 0 or lb.nblocks == 0:
-        return 0.0
+        return np.float64(0.0)
     lib = backend.get_lib()
     out = backend.scalar_out()
     if la.same_blocks(lb):
         lib.dot(la.size, a._buf, b._buf, backend.dot_scratch(), out)
-        return backend.read_scalar(out)
+        return np.float64(backend.read_scalar(out))
     # intersect the block tables
     qd = np.concatenate([la.qdata, lb.qdata], axis=0)
     order = _lexsort_rows(qd)
     qs = qd[order]
     same = np.nonzero(np.all(qs[1:] == qs[:-1], axis=1))[0]
     if len(same) == 0:
-        return 0.0
+        return np.float64(0.0)
     i1, i2 = order[same], order[same + 1]
     ia = np.where(i1 < la.nblocks, i1, i2)
     ib = np.where(i1 < la.nblocks, i2, i1) - la.nblocks
@@ -1284,7 +1331,7 @@ def inner(a, b, axes='labels', do_conj=False):
         lib.dot_segments(len(part), backend.to_device(part), int(part[:, 2].max()), a._buf, b._buf,
                          backend.dot_scratch(), out)
         total += backend.read_scalar(out)
-    return total
+    return np.float64(total)
 
 
 def norm(a, ord=None, convert_to_float=True):
@@ -1798,3 +1845,34 @@ def to_iterable_arrays(array_list):
 
 def concatenate_qdata(*a):  # pragma: no cover - placeholder for API completeness
     raise NotImplementedError
+
+
+# ---- the rest of the reference's surface (cold paths: model / MPO / site construction, indexing, complex tensors) ----------
+import sys as _sys
+
+from . import _surface as _sf
+from .charges import DipolarChargeInfo
+from ._surface import (QCUTOFF, grid_outer, grid_concat, detect_grid_outer_legcharge, detect_legcharge, eig, eigvals,
+                       speigs, expm, lq, polar, orthogonal_columns)
+
+Array.__getitem__ = _sf.array_getitem
+Array.__setitem__ = _sf.array_setitem
+Array.__iter__ = _sf.array_iter
+Array.__eq__ = _sf.array_eq
+Array.__hash__ = object.__hash__
+Array.permute = _sf.array_permute
+Array.sort_legcharge = _sf.array_sort_legcharge
+Array.unary_blockwise = _sf.array_unary_blockwise
+Array.iunary_blockwise = _sf.array_iunary_blockwise
+Array.binary_blockwise = _sf.array_binary_blockwise
+Array.ipurge_zeros = _sf.array_ipurge_zeros
+Array.from_func_square = classmethod(_sf.array_from_func_square)
+Array.add_charge = _sf.array_add_charge
+Array.drop_charge = _sf.array_drop_charge
+Array.change_charge = _sf.array_change_charge
+Array.shift_charges = _sf.array_shift_charges
+Array.shift_charges_horizontal = _sf.array_shift_charges_horizontal
+ComplexArray = _sf._finish_complex(_sys.modules[__name__])
+
+__all__ += ['DipolarChargeInfo', 'QCUTOFF', 'ComplexArray', 'grid_outer', 'grid_concat', 'detect_grid_outer_legcharge',
+            'detect_legcharge', 'eig', 'eigvals', 'speigs', 'expm', 'lq', 'polar', 'orthogonal_columns']

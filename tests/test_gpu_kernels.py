@@ -110,6 +110,34 @@ def test_block_svd(gpu_lib, shape):
     assert np.max(np.abs(backend.to_host(dA).reshape(m, n) - A)) == 0.0  # input untouched
 
 
+@pytest.fixture(params=[1, 3])
+def eig_variant(request, gpu_lib):
+    """both pivot eigen-solvers of the Jacobi rounds (csrc/svd.cu: 1 = shared memory, 3 = registers + shuffles)"""
+    old = gpu_lib.svd_set_eig_variant(request.param)
+    yield request.param
+    gpu_lib.svd_set_eig_variant(old)
+
+
+@pytest.mark.parametrize('shape', [(5, 5), (33, 47), (64, 64), (200, 150), (300, 512)])
+def test_block_svd_eig_variants(gpu_lib, eig_variant, shape):
+    """the block SVD with either pivot eigen-solver: singular values, reconstruction, orthogonality against LAPACK"""
+    from tenpy_b200 import backend
+    rng = np.random.default_rng(11)
+    m, n = shape
+    k = min(m, n)
+    A = rng.standard_normal((m, n)) * np.logspace(0, -5, n)[None, :]
+    dA = _dev(A.ravel())
+    dU, dS, dV = backend.zeros(m * k), backend.zeros(k), backend.zeros(k * n)
+    info, nact, _ = gpu_lib.block_svd([m], [n], [0], [0], [0], [0], dA, dU, dS, dV)
+    U, S, VT = backend.to_host(dU).reshape(m, k), backend.to_host(dS), backend.to_host(dV).reshape(k, n)
+    Sref = np.linalg.svd(A, compute_uv=False)
+    assert info[0] > 0 and nact[0] == k
+    assert np.max(np.abs(S - Sref)) < 1e-12 * Sref[0]
+    assert np.max(np.abs(U @ np.diag(S) @ VT - A)) < 1e-12 * Sref[0]
+    assert np.max(np.abs(U.T @ U - np.eye(k))) < 1e-12
+    assert np.max(np.abs(VT @ VT.T - np.eye(k))) < 1e-12
+
+
 def test_block_svd_batch_graded(gpu_lib):
     """several blocks of different shapes in one batch, with strongly graded singular values"""
     from tenpy_b200 import backend

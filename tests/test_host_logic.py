@@ -499,33 +499,3 @@ def test_matvec_identity_env(fake_device):
             'matvec_order': 'split', 'identity_env': True}
     res, psi = _run_dmrg(M, ['up', 'down'] * (L // 2), opts)
     assert abs(res['E'] - g['xxz_E']) < 1e-10 * abs(g['xxz_E'])
-
-
-def test_optins_switch(fake_device, monkeypatch):
-    """B200_OPTINS turns the opt-in routes on for a process (tenpy_b200/optins.py); a DMRG run with all of them gives the
-    golden energy"""
-    from tenpy_b200 import optins
-    from tenpy_b200.algorithms import mps_common
-    from tenpy_b200.linalg import krylov_based, np_conserved
-    from tenpy_b200.models import TFIChain
-    assert optins.requested('') == () and optins.requested('all') == optins.KNOWN
-    assert optins.requested('fused, identity') == ('fused', 'identity')
-    with pytest.raises(ValueError):
-        optins.requested('nonsense')
-    saved = (mps_common.TwoSiteH.mpo_apply, mps_common.TwoSiteH.identity_env, krylov_based.DEVICE_SCALARS_DEFAULT,
-             np_conserved.qr_method)
-    try:
-        assert optins.apply(optins.KNOWN, lib=fake_device) == optins.KNOWN
-        assert mps_common.TwoSiteH.mpo_apply == 'fused' and mps_common.TwoSiteH.identity_env is True
-        assert krylov_based.DEVICE_SCALARS_DEFAULT is True and np_conserved.qr_method == 'householder'
-        g = h.load('dmrg.npz')
-        M = TFIChain({'L': 20, 'J': 1., 'g': 1., 'conserve': None})
-        n0 = {k: fake_device.calls.get(k, 0) for k in ('mid_contract2', 'lanczos_update_dev')}
-        res, psi = _run_dmrg(M, ['up'] * 20, {'mixer': None, 'max_E_err': 1e-10, 'combine': True, 'matvec_order': 'split',
-                                             'trunc_params': {'chi_max': 50, 'svd_min': 1e-10}})
-        assert abs(res['E'] - g['tfi_E']) < 1e-10 * abs(g['tfi_E'])
-        assert fake_device.calls.get('mid_contract2', 0) > n0['mid_contract2']
-        assert fake_device.calls.get('lanczos_update_dev', 0) > n0['lanczos_update_dev']
-    finally:
-        (mps_common.TwoSiteH.mpo_apply, mps_common.TwoSiteH.identity_env, krylov_based.DEVICE_SCALARS_DEFAULT,
-         np_conserved.qr_method) = saved
