@@ -229,6 +229,9 @@ class TwoSiteH:
         """``LP . theta . (W0 W1) . RP`` on the split legs; interface (labels, pipes) of the combined matvec."""
         if self._W01 is None:
             self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])   # wL p0 p0* p1 p1* wR  (D^2 d^4 numbers)
+        rec = getattr(self, '_dense_recipe', None)
+        if rec is not None and theta._layout is rec['lay'] and theta._labels == rec['labels']:
+            return self._dense_recipe_run(theta, rec)
         th = theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)            # vL p0 p1 vR (read only here)
         if self.identity_env and getattr(self, '_id_env', None) is not False:
             try:
@@ -328,7 +331,9 @@ class TwoSiteH:
                 out.ireplace_labels(['vR*', 'vL*'], ['vL', 'vR'])
                 out.iadd_prefactor_other(1., y_id.ireplace_label('vR*', 'vL'))
                 out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
-                return out.itranspose(labels)
+                out = out.itranspose(labels)
+                self._dense_recipe_record(th, t1, y_rest, y_id, out)
+                return out
         n0_single = int(t1._layout.size) if (t1._layout.nblocks == 1 and not t1._layout.has_padding) else None
         th_id = th.add_leg(self._leg_IdL, 0, axis=1, label='wR').ireplace_label('vL', 'vR*')
         t1 = npc.concatenate([t1, th_id], axis='wR')                         # wR: [others ..., IdL]
@@ -354,6 +359,57 @@ class TwoSiteH:
         out.iadd_prefactor_other(1., direct)
         out = out.combine_legs([['vL', 'p0'], ['p1', 'vR']], pipes=[self.pipeL, self.pipeR], _view=True)
         return out.itranspose(labels)
+
+    # The dense (no charges, one block per tensor) identity-environment matvec is always the same six kernels: split theta,
+    # int8 GEMM with LP_rest, W0 W1 streaming pass, split, int8 GEMM with RP_rest, axpy.  Going through the Array layer
+    # (label bookkeeping, leg checks, plan look-ups, result objects) costs ~1 ms of Python per matvec -- as much as the
+    # kernels take at chi = 1024 -- so after the first call of a bond the raw sequence is replayed on the buffers.
+    def _dense_recipe_record(self, th, t1, y_rest, y_id, out):
+        if getattr(self, '_dense_recipe', None) is not None or self._dense_recipe_off:
+            return
+        from .. import backend
+        arrs = (th, t1, y_rest, y_id, out, self._LP_rest, self._RP_rest_t)
+        if any(a._layout.nblocks != 1 for a in arrs) or np.any(out.qtotal != th.qtotal):
+            self._dense_recipe_off = True
+            return
+        chi_l, Dm1, d0, d1, chi_r = t1.shape
+        if self._LP_rest.shape != (chi_l, Dm1, chi_l) or self._RP_rest_t.shape != (Dm1, chi_r, chi_r) or \
+                out._layout.size != th._layout.size:
+            self._dense_recipe_off = True
+            return
+        plan1 = npc._PLAN_CACHE.get((self._LP_rest._layout.uid, th._layout.uid, 1))
+        plan2 = npc._PLAN_CACHE.get((y_rest._layout.uid, self._RP_rest_t._layout.uid, 2))
+        if plan1 is None or plan2 is None:
+            self._dense_recipe_off = True
+            return
+        self._dense_recipe = {
+            'lay': out._layout, 'labels': list(out._labels), 'template': out,
+            'g1': (chi_l * Dm1, d0 * d1 * chi_r, chi_l), 'plan1': plan1[2],          # (m, n, k) of LP_rest . theta
+            'g2': (chi_l * d0 * d1, chi_r, Dm1 * chi_r), 'plan2': plan2[2],          # y_rest . RP_rest
+            'mid': (Dm1 * d0 * d1, d0 * d1, self._N1, d0 * d1, chi_l, chi_r),
+            'n_t1': int(t1._layout.size), 'n_yr': int(y_rest._layout.size), 'n_yi': int(y_id._layout.size),
+            # buffers whose size is not a multiple of the block alignment carry zero padding (BLAS-1 runs over it)
+            'alloc': backend.zeros if any(a._layout.has_padding for a in (t1, y_rest, y_id, out)) else backend.empty,
+        }
+
+    _dense_recipe_off = False
+
+    def _dense_recipe_run(self, theta, rec):
+        from .. import backend
+        lib = backend.get_lib()
+        s = npc.OZAKI['slices_matvec']
+        alloc = rec['alloc']
+        t1 = alloc(rec['n_t1'])
+        npc._raw_product(lib, self._LP_rest, theta, rec['g1'], rec['plan1'], t1, s)
+        y_r, y_i = alloc(rec['n_yr']), alloc(rec['n_yi'])
+        K1, K2, N1, N2, chi_l, chi_r = rec['mid']
+        lib.mid_contract2(K1, K2, N1, N2, chi_l, chi_r, self._M_id, t1, theta._buf, y_r, y_i)
+        out = alloc(rec['lay'].size)
+        npc._raw_product(lib, y_r, self._RP_rest_t, rec['g2'], rec['plan2'], out, s)
+        lib.axpy(rec['lay'].size, 1., y_i, out)
+        res = rec['template'].copy(deep=False)
+        res._buf = out
+        return res
 
     @staticmethod
     def _split_t2_views(t2):

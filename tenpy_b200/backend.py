@@ -38,6 +38,7 @@ def use_library(lib):
     npc = sys.modules.get('tenpy_b200.linalg.np_conserved')
     if npc is not None:
         npc._PLAN_CACHE.clear()
+        npc._EMPTY_LAYOUTS.clear()
     return lib
 
 

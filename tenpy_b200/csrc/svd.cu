@@ -359,6 +359,41 @@ __global__ void __launch_bounds__(JTHREADS)
 //     4. Q <- Q J^T (columns p, q of every row: lanes p, q of the same warp, shuffle);
 //     5. write G'' to sA for the parameters of the next set, barrier.
 // Same interface and the same rotations (to rounding) as version 1.
+// Jacobi rotation (c, s) that annihilates g_pq:  t = tan(theta) = sign(z) / (|z| + sqrt(1 + z^2)),  z = (g_qq - g_pp) / (2 g_pq),
+// c = 1 / sqrt(1 + t^2), s = t c  (the same rotation as version 1).  The double-precision sqrt / division / rsqrt of the
+// straightforward formula are ~100-instruction dependent chains each and sit on the critical path of every rotation set;
+// here each is a single-precision hardware approximation refined by two Newton steps in double precision (relative error
+// ~1e-15; c^2 + s^2 = 1 to rounding by construction, so the transformation stays orthogonal whatever the error of t).
+__device__ __forceinline__ double jeig3_rcp(double x) {          // 1/x for |x| in [1e-30, 1e30]
+    double r = (double)__frcp_rn((float)x);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double jeig3_rsqrt(double x) {        // 1/sqrt(x) for x in [1, 1e30]
+    double r = (double)rsqrtf((float)x);
+    r = r * fma(-0.5 * x, r * r, 1.5);
+    return r * fma(-0.5 * x, r * r, 1.5);
+}
+__device__ __forceinline__ void jeig3_rotation(double gpp, double gqq, double gpq, double &c, double &s) {
+    const double aa = gqq - gpp, bb = 2.0 * gpq;
+    // bring bb to [1, 2) by a power of two (exact) so that the single-precision seed cannot over- or underflow
+    int eb = (int)((__double_as_longlong(bb) >> 52) & 0x7ff);
+    eb = min(max(eb, 2), 2044);
+    const double scale = __longlong_as_double((long long)(2046 - eb) << 52);
+    const double z = (aa * scale) * jeig3_rcp(bb * scale);
+    const double az = fabs(z);
+    double t;
+    if (az < 1.e12) {
+        const double y = fma(z, z, 1.0);
+        const double den = az + y * jeig3_rsqrt(y);               // |z| + sqrt(1 + z^2), in [1, 2e12]
+        t = copysign(jeig3_rcp(den), z);
+    } else {
+        t = 0.5 / z;                                              // also covers z = +-inf (t = 0)
+    }
+    c = jeig3_rsqrt(fma(t, t, 1.0));
+    s = t * c;
+}
+
 __device__ __forceinline__ int jeig3_partner(int x, int step) {
     // round-robin tournament over JP = 32 indices, index 31 fixed: pairs (31, step) and ((step+j) % 31, (step-j) % 31)
     if (x == JP - 1) return step;
@@ -395,6 +430,7 @@ __global__ void __launch_bounds__(JTHREADS)
         for (int i = 0; i < 4; ++i) {
             const int c = 4 * warp + i;
             double v = 0.0;
+#pragma unroll 4
             for (int sp = 0; sp < ns; ++sp) v += G[sp * (JP * JP) + c * JP + lane];   // G[c][l] = G[l][c], coalesced
             g[i] = v;
             sA[lane * JLDG + c] = v;
@@ -434,12 +470,8 @@ __global__ void __launch_bounds__(JTHREADS)
             const int p = is_p ? lane : partner, q = is_p ? partner : lane;
             const double gpp = sA[p * JLDG + p], gqq = sA[q * JLDG + q], gpq = sA[p * JLDG + q];
             double c = 1.0, sn = 0.0;
-            if (fabs(gpq) > tol_in * sqrt(fabs(gpp * gqq)) && gpp > defl2 && gqq > defl2) {
-                const double aa = gqq - gpp, bb = 2.0 * gpq;
-                const double hh = sqrt(aa * aa + bb * bb);
-                const double tt = (aa >= 0.0) ? bb / (aa + hh) : bb / (aa - hh);
-                c = rsqrt(1.0 + tt * tt);
-                sn = tt * c;
+            if (gpq * gpq > (tol_in * tol_in) * fabs(gpp * gqq) && gpp > defl2 && gqq > defl2) {
+                jeig3_rotation(gpp, gqq, gpq, c, sn);
                 if (warp == 0) s_any = 1;     // benign race: every writer stores 1
             }
             // row p: c x_p - s x_q ;  row q: s x_p + c x_q   -> as "own * c + other * (-s | +s)"

@@ -33,6 +33,8 @@ __all__ = ['QTYPE', 'ChargeInfo', 'LegCharge', 'LegPipe', 'Array', 'zeros', 'eye
            'concatenate', 'ones', 'detect_qtotal', 'qr']
 
 _PLAN_CACHE = {}
+_EMPTY_LAYOUTS = {}      # rank -> the (interned) layout without blocks
+_F64 = np.dtype(np.float64)
 svd_stats = {'calls': 0, 'jacobi_sweeps': []}   # diagnostics: Jacobi sweeps used by each npc.svd call
 _PLAN_CACHE_MAX = 16384
 
@@ -116,17 +118,24 @@ class Array:
     """
 
     def __init__(self, legcharges, dtype=np.float64, qtotal=None, labels=None):
-        self.legs = list(legcharges)
-        self._set_shape()
-        self.dtype = np.dtype(dtype)
-        if self.dtype != np.float64:
-            raise NotImplementedError('tenpy_b200 supports float64 Arrays only (got {0})'.format(self.dtype))
-        self.chinfo = self.legs[0].chinfo if self.rank else ChargeInfo()
-        self.qtotal = self.chinfo.make_valid(qtotal)
-        self._labels = [None] * self.rank
-        if labels is not None:
+        self.legs = legs = list(legcharges)
+        self.rank = rank = len(legs)
+        self.shape = tuple([int(l.ind_len) for l in legs])
+        if dtype is not np.float64 and np.dtype(dtype) != np.float64:
+            raise NotImplementedError('tenpy_b200 supports float64 Arrays only (got {0}); complex tensors: '
+                                      'ComplexArray'.format(np.dtype(dtype)))
+        self.dtype = _F64
+        self.chinfo = chinfo = legs[0].chinfo if rank else ChargeInfo()
+        self.qtotal = chinfo.make_valid(qtotal)
+        if labels is None:
+            self._labels = [None] * rank
+        else:
+            self._labels = [None] * rank
             self.iset_leg_labels(labels)
-        self._layout = BlockLayout(np.zeros((0, self.rank), np.int64), np.zeros((0, self.rank), np.int64))
+        lay = _EMPTY_LAYOUTS.get(rank)
+        if lay is None:
+            lay = _EMPTY_LAYOUTS[rank] = BlockLayout(np.zeros((0, rank), np.int64), np.zeros((0, rank), np.int64))
+        self._layout = lay
         self._buf = None
         self._qdata_sorted = True
 
@@ -1203,6 +1212,22 @@ def _oz_split_operand(lib, arr, role, rows, k, off, slices):
     if cache is not None:
         cache[key] = sp
     return sp
+
+
+def _raw_product(lib, a, b, geom, plan, out, slices=None):
+    """one dense block product ``out (m x n) = A (m x k) . B (k x n)`` on raw buffers (internal; replay of recorded
+    kernel sequences, see TwoSiteH._dense_recipe_run): `a` / `b` are Arrays (their int8 digit planes are cached when the
+    owner declared them constant) or bare device buffers; int8 tensor path when it applies, else the DMMA plan"""
+    m, n, k = geom
+    if OZAKI['enabled'] and 2. * m * n * k >= OZAKI['min_flops'] and min(m, n, k) >= OZAKI['min_dim'] and \
+            hasattr(lib, 'ozaki_mm'):
+        s = int(slices or OZAKI['slices'])
+        a_s = _oz_split_operand(lib, a, 'A', m, k, 0, s) if isinstance(a, Array) else lib.ozaki_split(m, k, a, k, 1, s)
+        b_s = _oz_split_operand(lib, b, 'B', n, k, 0, s) if isinstance(b, Array) else lib.ozaki_split(n, k, b, 1, n, s)
+        lib.ozaki_mm(m, n, k, s, a_s, b_s, out, n)
+        OZAKI['calls'] += 1
+    else:
+        plan.run(a._buf if isinstance(a, Array) else a, b._buf if isinstance(b, Array) else b, out)
 
 
 def _tensordot_int8(a, b, plan, buf, slices=None):

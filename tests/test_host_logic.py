@@ -477,6 +477,15 @@ def test_matvec_identity_env(fake_device):
         a, b = Hc.matvec(theta), Hf.matvec(theta)
         assert fake_device.calls.get('mid_contract2', 0) == n0 + 1
         assert npc.norm(a - b) <= 1e-11 * max(npc.norm(a), 1e-300)
+        # second call on the same bond: the recorded raw kernel sequence is replayed (no Array-level bookkeeping)
+        assert Hf._dense_recipe is not None
+        n_plan = fake_device.calls.get('tdot_plan', 0)
+        c = Hf.matvec(theta)
+        assert fake_device.calls.get('mid_contract2', 0) == n0 + 2 and fake_device.calls.get('tdot_plan', 0) == n_plan
+        assert c.get_leg_labels() == b.get_leg_labels() and c._layout is b._layout
+        assert npc.norm(c - b) <= 1e-14 * max(npc.norm(b), 1e-300)
+        c2 = Hf.matvec(theta * 2.)
+        assert npc.norm(c2 - 2. * b) <= 1e-13 * max(npc.norm(b), 1e-300)
     # not applicable: an environment whose IdL component is not the identity -> the plain split order, same result
     H = TwoSiteH(eng.env, 2, combine=True, matvec_order='split')
     H.identity_env = True
