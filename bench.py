@@ -61,6 +61,11 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-blocksparse', action='store_true', help='skip the configs[2]/[3] shaped matvec probes')
+    ap.add_argument('--ref-budget-s', type=float, default=240., help='--impl reference: wall-clock budget of the measured steps')
+    ap.add_argument('--scan', default='auto', choices=['auto', 'on', 'off'],
+                    help='BASELINE.json configs[4]: chi in {256,512,1024,2048} x two fields, sharded over the ranks by LPT '
+                         '(tenpy_b200.scan); auto = on for N > 1')
+    ap.add_argument('--scan-chis', default='256,512,1024,2048')
     return ap.parse_args()
 
 
@@ -305,6 +310,63 @@ class ReferenceArm:
         return dt / n_bonds
 
 
+def reference_components_sample(args, budget_s=40.):
+    """`cpu_baseline` of the GPU arm's line: the pieces of ONE centre-bond update timed on the unmodified reference's own
+    engine (tenpy.linalg.np_conserved from baseline/_ref: `npc.tensordot` for the two contractions of `TwoSiteH.matvec`,
+    `npc.svd` of the two-site wave function of the benchmark state), without building the 2 x 49 environments a real sweep
+    needs (the `--impl reference` arm does that): bond = N_lanczos matvecs + SVD + environment update (3/4 matvec,
+    SURVEY.md section 8a9).  Returns None when no reference is installed."""
+    from tenpy_b200 import dropin
+    path = dropin.reference_path()
+    if path is None or dropin.installed():
+        return None
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import tenpy.linalg.np_conserved as npc
+    from threadpoolctl import threadpool_limits
+    chi, d, D, L = args.chi, 2, 3, args.L
+    n = chi * d
+    rng = np.random.default_rng(0)
+    Bs, Ss = synthetic_tensors_host(L, chi, d, seed=0)
+    c = L // 2 - 1
+    th = np.tensordot(Ss[c][:, None, None] * Bs[c], Bs[c + 1], axes=[2, 0]).reshape(n, n)     # theta of the benchmark state
+    del Bs
+    LH = rng.standard_normal((n, D, n))
+    RH = rng.standard_normal((D, n, n))
+    LHeff = npc.Array.from_ndarray_trivial(LH + LH.transpose(2, 1, 0), labels=['(vR*.p0)', 'wR', '(vR.p0*)'])
+    RHeff = npc.Array.from_ndarray_trivial(RH, labels=['wL', '(p1*.vL)', '(p1.vL*)'])
+    theta = npc.Array.from_ndarray_trivial(th, labels=['(vL.p0)', '(p1.vR)'])
+    del LH, RH
+
+    def matvec(x):           # tenpy/algorithms/mps_common.py:1337-1339
+        x = npc.tensordot(LHeff, x, axes=['(vR.p0*)', '(vL.p0)'])
+        return npc.tensordot(x, RHeff, axes=[['wR', '(p1.vR)'], ['wL', '(p1*.vL)']])
+    ncpu = os.cpu_count() or 1
+    res, t_used = {}, time.perf_counter()
+    for t in sorted(set([x for x in (8, 32) if x < ncpu] + [ncpu])):
+        with threadpool_limits(limits=t):
+            matvec(theta)
+            t0 = time.perf_counter()
+            matvec(theta)
+            t_mv = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            npc.svd(theta, inner_labels=['vR', 'vL'])
+            t_svd = time.perf_counter() - t0
+        res[t] = {'matvec_s': t_mv, 'svd_s': t_svd, 'bond_s': (args.lanczos_N + 0.75) * t_mv + t_svd}
+        if time.perf_counter() - t_used > budget_s:
+            break
+    best = min(res, key=lambda t: res[t]['bond_s'])
+    full = n_full_bonds(L, chi, d)
+    return {'value': res[best]['bond_s'] * full, 'unit': UNIT, 'cores': best, 'kind': 'reference',
+            'sample': 'unmodified tenpy engine (%s): 1 effective-H matvec (LHeff.theta.RHeff, 4 D d^3 chi^3 flop) and 1 npc.svd '
+                      'of the centre two-site wave function of the benchmark state, best of BLAS threads %s; bond = %d matvecs '
+                      '+ SVD + 0.75 matvec (environment update), x %d full-chi bonds per sweep'
+                      % (path, sorted(res), args.lanczos_N, full),
+            'per_bond_s': res[best]['bond_s'], 'matvec_s': res[best]['matvec_s'], 'svd_s': res[best]['svd_s'],
+            'matvec_gflops': 4. * D * d**3 * float(chi)**3 / res[best]['matvec_s'] / 1e9, 'thread_sweep': {str(k): v for k, v in res.items()},
+            'host_cpus': ncpu, 'extrapolated': True}
+
+
 def _bond_svs(Ss, L):
     """singular values on the L+1 bonds for MPS.from_Bflat (form 'B': S[i] is left of site i)"""
     return [Ss[i] for i in range(L)] + [np.ones(1)]
@@ -330,13 +392,21 @@ def run_reference(args):
         cores, extra = blas_threads(), {'fallback_reason': why, 'matvec_s': vals[0]['matvec_s']}
         sample = '1 centre-bond update per step with the dense numpy port oracle/dmrg_dense.py (reference not installed here)'
     else:
+        t_start = time.perf_counter()
         arm.step(1)                               # builds the 2 x 49 environments up to the centre (not timed)
         threads = arm.choose_threads()
-        per = []
+        # one bond update of this workload takes 5-50 s on the host (LAPACK on a numerically low-rank 2048 x 2048 theta), so
+        # the K + W steps the driver asks for are measured within a time budget; later steps reuse the mean so far
+        per, skipped = [], 0
         for it in range(args.warmup + args.steps):
+            if per and time.perf_counter() - t_start > args.ref_budget_s:
+                skipped += 1
+                continue
             dt = arm.step(1)
-            if it >= args.warmup:
+            if it >= args.warmup or (it == args.warmup + args.steps - 1 and not per):
                 per.append(dt)
+            elif time.perf_counter() - t_start > args.ref_budget_s and not per:
+                per.append(dt)                    # the budget is gone after the warm-up steps: their last one counts
         per_bond = float(np.mean(per))
         full = n_full_bonds(args.L, args.chi, 2)
         cores = threads
@@ -345,7 +415,8 @@ def run_reference(args):
                  'thread_sweep': {str(k): v for k, v in sw.items()}, 'matvec_s': sw[threads]['matvec_s'],
                  'svd_s': sw[threads]['svd_s'],
                  'matvec_gflops': 4. * 3 * 8 * float(args.chi)**3 / sw[threads]['matvec_s'] / 1e9,
-                 'per_bond_s_each_step': per}
+                 'per_bond_s_each_step': per, 'steps_measured': len(per), 'steps_not_run_time_budget': skipped,
+                 'time_budget_s': args.ref_budget_s}
         sample = ('1 bond update at the chain centre per step through the unmodified tenpy TwoSiteDMRGEngine.sweep() '
                   '(schedule restricted to that bond; %d Lanczos matvecs LHeff.theta.RHeff + LAPACK SVD + environment '
                   'update, %d BLAS threads = best of the thread sweep), x %d full-chi bonds of a sweep'
@@ -513,6 +584,27 @@ def run_b200(args):
         finally:
             eng.options.pop('identity_env', None)
 
+    # ---- the same state with the reference's DEFAULT Lanczos settings (N_min=2, N_max=20, convergence by P_tol): a converged
+    #      DMRG needs 2-3 matvecs per bond instead of the harness' fixed 10, so SVD / block moves / host latencies weigh more
+    default_lanczos = {}
+    try:
+        opts2 = dict(opts)
+        opts2['lanczos_params'] = {}
+        eng2 = dmrg.TwoSiteDMRGEngine(psi, model, opts2)
+        eng2.sweep()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        b0.record()
+        eng2.sweep()
+        b1.record()
+        torch.cuda.synchronize()
+        default_lanczos = {'sweep_s': b0.elapsed_time(b1) / 1e3,
+                           'N_lanczos_mean': float(np.mean(eng2.update_stats['N_lanczos'][-2 * (L - 2):])),
+                           'E': float(eng2.update_stats['E_total'][-1])}
+        del eng2
+    except Exception as e:   # never lose the bench line
+        default_lanczos = {'error': repr(e)}
+
     # ---- one more sweep with per-family CUDA-event profiling (after the timed one: same, converged regime; the
     #      event pairs bracket every library call, so host gaps inside a call -- the SVD reads q doubles per Jacobi
     #      sweep -- count for that family)
@@ -543,6 +635,16 @@ def run_b200(args):
     mv_orders = matvec_order_probe(eng, psi, L, chi, d, D)
     roof['svd']['workload_theta'] = svd_theta_probe(eng, psi, L)
     bs_probes = blocksparse_probes(small=(chi < 256)) if not args.no_blocksparse else None
+
+    # ---- BASELINE.json configs[4]: the unequal-chi scan, sharded over the ranks (after the equal-work measurement)
+    scan_res = None
+    if args.scan == 'on' or (args.scan == 'auto' and world > 1):
+        del eng, psi
+        torch.cuda.empty_cache()
+        try:
+            scan_res = run_chi_scan(args, lib, world, rank)
+        except Exception as e:   # never lose the bench line
+            scan_res = {'error': repr(e)}
 
     # ---- gather over ranks
     stats = torch.tensor([ms, E_final, S_mid, e2e['value'] if e2e else 0.], dtype=torch.float64, device=lib.device)
@@ -581,6 +683,7 @@ def run_b200(args):
             'kernel_time_shares': shares, 'kernel_family_ms_per_sweep': {k: round(v[1], 2) for k, v in prof.items()},
             'matvec_orders': mv_orders, 'matvec_gflops': _matvec_gflops(mv_orders),
             'blocksparse_matvec': bs_probes, 'ab': ab, 'identity_env_stats': id_stats, 'peaks': peaks_kind, 'parity': parity,
+            'chi_scan': scan_res, 'reference_default_lanczos': default_lanczos,
             'result': {'E': [float(x) for x in allst[:, 1]], 'S_mid': [float(x) for x in allst[:, 2]],
                        'N_lanczos_mean': N_lan, 'svd_jacobi_sweeps_mean': float(np.mean(jsw)),
                        'svd_jacobi_sweeps_max': int(np.max(jsw)), 'svd_calls': svd_stats['calls'],
@@ -590,20 +693,68 @@ def run_b200(args):
                        'svd_subspace_residual_median': float(np.median(sub_stats['residuals'][-2 * (L - 2):]))
                        if sub_stats['residuals'] else None}}
     if not args.no_cpu:
-        est = cpu_sweep_estimate(args, args.cpu_bonds)
-        line['cpu_baseline'] = {'value': est['sweep_s'], 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
-                                'sample': '%d centre-bond updates (oracle/dmrg_dense.py, numpy/OpenBLAS/LAPACK gesdd; '
-                                          'Lanczos matvec in the faster of the two reference contraction orders: %s) '
-                                          'x %d full-chi bonds per sweep' % (args.cpu_bonds, est['matvec_order_used'],
-                                                                             est['full_chi_bonds']),
-                                'per_bond_s': est['per_bond_s'], 'matvec_gflops': est['matvec_gflops'],
-                                'matvec_s': est['matvec_s'], 'matvec_split_s': est['matvec_split_s']}
+        cb = None
+        try:
+            cb = reference_components_sample(args)
+        except Exception as e:      # never lose the bench line
+            cb = None
+            line['cpu_baseline_reference_error'] = repr(e)
+        if cb is None:
+            est = cpu_sweep_estimate(args, args.cpu_bonds)
+            cb = {'value': est['sweep_s'], 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
+                  'sample': '%d centre-bond updates (oracle/dmrg_dense.py, numpy/OpenBLAS/LAPACK gesdd; Lanczos matvec in '
+                            'the faster of the two reference contraction orders: %s) x %d full-chi bonds per sweep'
+                            % (args.cpu_bonds, est['matvec_order_used'], est['full_chi_bonds']),
+                  'per_bond_s': est['per_bond_s'], 'matvec_gflops': est['matvec_gflops'],
+                  'matvec_s': est['matvec_s'], 'matvec_split_s': est['matvec_split_s']}
+        line['cpu_baseline'] = cb
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     if not parity['ok']:
         sys.stderr.write('bench.py: energy parity FAILED: rel. err %r > 1e-10\n' % (E_err,))
         sys.exit(3)
+
+
+def run_chi_scan(args, lib, world, rank):
+    """BASELINE.json configs[4]: 8 independent DMRG runs, chi in {256, 512, 1024, 2048} x g in {0.9, 1.1}, sharded over the
+    ranks with `tenpy_b200.scan` (largest estimated cost chi^3 first, always to the least loaded rank).  Each run = the
+    benchmark's workload at its own chi: synthetic state, one warm-up sweep, one timed sweep (CUDA events).  Returns on
+    rank 0 the per-run table, the per-rank busy times and the load-balance efficiency (mean / max rank time)."""
+    import torch
+    from tenpy_b200 import scan
+    from tenpy_b200.models import TFIChain
+    from tenpy_b200.algorithms import dmrg
+    chis = [int(x) for x in args.scan_chis.split(',')]
+    configs = [{'chi': c, 'g': g} for c in chis for g in (0.9, 1.1)]
+
+    def run(cfg):
+        model = TFIChain({'L': args.L, 'J': 1., 'g': cfg['g'], 'conserve': None})
+        psi = synthetic_mps(model, args.L, cfg['chi'], 2, seed=cfg['chi'])
+        opts = {'mixer': None, 'combine': True, 'diag_method': 'lanczos', 'svd_warm_start': False,
+                'trunc_params': {'chi_max': cfg['chi'], 'svd_min': 1e-45, 'trunc_cut': None},
+                'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N}}
+        eng = dmrg.TwoSiteDMRGEngine(psi, model, opts)
+        eng.sweep()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        eng.sweep()
+        ev1.record()
+        torch.cuda.synchronize()
+        E = float(eng.update_stats['E_total'][-1])
+        del eng, psi
+        torch.cuda.empty_cache()
+        return [cfg['chi'], cfg['g'], ev0.elapsed_time(ev1) / 1e3, E, rank]
+    table = scan.run_scan(configs, run, cost_fn=lambda c: float(c['chi'])**3)
+    if rank != 0:
+        return None
+    per_rank = [float(np.sum(table[table[:, 5] == r, 3])) for r in range(world)]
+    return {'runs': [{'chi': int(r[1]), 'g': float(r[2]), 'sweep_s': float(r[3]), 'E': float(r[4]), 'rank': int(r[5])}
+                     for r in table],
+            'rank_busy_s': per_rank, 'makespan_s': max(per_rank),
+            'load_balance_efficiency': float(np.mean(per_rank) / max(per_rank)) if max(per_rank) > 0 else None,
+            'assignment': 'LPT on chi^3 (tenpy_b200.scan.assign_runs)', 'sweeps_per_run': '1 warm-up + 1 timed'}
 
 
 def _matvec_gflops(mv_orders):

@@ -258,6 +258,77 @@ static int run_rate(int N, int nacc, int ctas, int layout = 2, uint32_t lbo = 16
     return 0;
 }
 
+
+// ---- fragment layout of tcgen05.ld.16x256b: write lane*1000 + column with 32x32b stores, read back with 16x256b.x2 ----
+__global__ void __launch_bounds__(128, 1) ldshape_kernel(int32_t *out) {
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 64);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_slot;
+    {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (uint32_t)((warp * 32 + lane) * 1000 + j);
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+            "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(tmem + ((uint32_t)(warp * 32) << 16)),
+            "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+            "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+            "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+            "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    // every warp reads its own lane quarter, lower (h = 0) and upper (h = 1) 16 lanes: 16x256b.x2 = 16 columns, 8 registers
+    for (int h = 0; h < 2; ++h) {
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(tmem + ((uint32_t)(warp * 32 + h * 16) << 16))
+                     : "memory");
+        tmem_ld_wait();
+        for (int j = 0; j < 8; ++j) out[((warp * 2 + h) * 32 + lane) * 8 + j] = (int32_t)r[j];
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+static int run_ldshape() {
+    int32_t *d;
+    CK(cudaMalloc(&d, 4 * 2 * 32 * 8 * 4));
+    ldshape_kernel<<<1, 128>>>(d);
+    CK(cudaDeviceSynchronize());
+    std::vector<int32_t> h(4 * 2 * 32 * 8);
+    CK(cudaMemcpy(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost));
+    // expected (mma m16n8 accumulator layout per 8-column group g): r[4g+0], r[4g+1] = row lane/4, cols 8g + 2(lane%4) + {0,1};
+    // r[4g+2], r[4g+3] = row lane/4 + 8, same columns
+    long bad = 0;
+    for (int w = 0; w < 4; ++w)
+        for (int hh = 0; hh < 2; ++hh)
+            for (int l = 0; l < 32; ++l)
+                for (int j = 0; j < 8; ++j) {
+                    int g = j / 4, i = j % 4;
+                    int row = w * 32 + hh * 16 + l / 4 + (i >= 2 ? 8 : 0), col = 8 * g + 2 * (l % 4) + (i & 1);
+                    if (h[(((w * 2 + hh) * 32 + l) * 8) + j] != row * 1000 + col) ++bad;
+                }
+    printf("ldshape 16x256b.x2: %ld of %d registers differ from the m16n8 accumulator layout\n", bad, 4 * 2 * 32 * 8);
+    for (int l = 0; l < 8; ++l) {
+        printf("  warp 1, lower half, lane %d:", l);
+        for (int j = 0; j < 8; ++j) printf(" %d", h[(((1 * 2 + 0) * 32 + l) * 8) + j]);
+        printf("\n");
+    }
+    cudaFree(d);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
     int fails = 0;
     const char *mode = argc > 1 ? argv[1] : "all";
@@ -286,6 +357,7 @@ int main(int argc, char **argv) {
         run_rate(128, 4, 148, 4, 16, 512, 32, 2, "sw64");
         run_rate(128, 4, 148, 6, 16, 256, 32, 1, "sw32");
     }
+    if (!strcmp(mode, "all") || !strcmp(mode, "ldshape")) run_ldshape();
     printf("probe %s (%d failing sw128 cases)\n", fails ? "FAILED" : "ok", fails);
     return fails ? 1 : 0;
 }

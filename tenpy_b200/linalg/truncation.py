@@ -12,7 +12,7 @@ import numpy as np
 
 from . import np_conserved as npc
 
-__all__ = ['TruncationError', 'truncate', 'svd_theta', 'decompose_theta_qr_based']
+__all__ = ['TruncationError', 'truncate', 'svd_theta']
 
 
 class TruncationError:
@@ -51,60 +51,68 @@ class TruncationError:
         return 'TruncationError(eps={0:.4e}, ov={1:.10f})'.format(self.eps, self.ov)
 
 
-def _combine_constraints(good1, good2, warn):
-    """Logical and of two constraints, unless that leaves nothing (reference truncation.py:719)."""
-    res = np.logical_and(good1, good2)
-    if np.any(res):
-        return res
-    warnings.warn('truncation: can not satisfy constraint for ' + warn, stacklevel=3)
-    return good1
+class _KeepCounts:
+    """The admissible numbers of kept Schmidt values, narrowed rule by rule.  A rule that would leave no admissible count is
+    skipped with a warning (behaviour of the reference's constraint chain, truncation.py:719-731)."""
+
+    def __init__(self, n):
+        self.ok = np.ones(n + 1, dtype=np.bool_)     # ok[k]: keeping the k largest values is admissible
+        self.ok[0] = False                            # at least one value is always kept
+
+    def require(self, allowed, rule):
+        both = self.ok & allowed
+        if both.any():
+            self.ok = both
+        else:
+            warnings.warn('truncation: can not satisfy constraint for ' + rule, stacklevel=4)
+
+    def largest(self):
+        return int(np.nonzero(self.ok)[0][-1])
 
 
 def truncate(S, options):
-    """Decide which Schmidt values to keep (reference truncation.py:146).
+    """Which Schmidt values survive a truncation (reference truncation.py:146; same options, defaults and results).
 
-    Options: `chi_max` (100), `chi_min`, `degeneracy_tol`, `svd_min` (1e-14), `trunc_cut` (1e-14).
-    Returns ``(mask, norm_new, TruncationError)``."""
-    chi_max = options.get('chi_max', 100)
-    chi_min = options.get('chi_min', None)
-    deg_tol = options.get('degeneracy_tol', None)
-    svd_min = options.get('svd_min', 1.e-14)
-    trunc_cut = options.get('trunc_cut', 1.e-14)
+    The values are ranked in descending order and every option turns into a condition on the NUMBER k of kept values:
+    ``chi_max``: k <= chi_max; ``chi_min``: k >= chi_min; ``degeneracy_tol``: no cut between two values whose logarithms are
+    closer than the tolerance; ``svd_min``: only values >= svd_min; ``trunc_cut``: the discarded weight
+    ``sum_{i >= k} S_i^2`` stays <= trunc_cut^2.  The largest admissible k wins; conditions are imposed in this order and a
+    condition that contradicts the earlier ones is dropped with a warning.  Returns ``(mask, norm_new, TruncationError)``."""
+    chi_max, chi_min = options.get('chi_max', 100), options.get('chi_min', None)
+    deg_tol, svd_min, trunc_cut = options.get('degeneracy_tol', None), options.get('svd_min', 1.e-14), \
+        options.get('trunc_cut', 1.e-14)
     if trunc_cut is not None and trunc_cut >= 1.:
         raise ValueError('trunc_cut >=1.')
     S = np.asarray(S)
-    if not np.any(S > 1.e-10):
+    n = len(S)
+    if not (S > 1.e-10).any():
         warnings.warn('no Schmidt value above 1.e-10', stacklevel=2)
-    if np.any(S < -1.e-10):
+    if (S < -1.e-10).any():
         warnings.warn('negative Schmidt values!', stacklevel=2)
-    logS = np.log(np.choose(S <= 0., [S, 1.e-100 * np.ones(len(S))]))
-    piv = np.argsort(logS)
-    logS = logS[piv]
-    good = np.ones(len(piv), dtype=np.bool_)
+    logs = np.log(np.where(S > 0., S, 1.e-100))
+    rank = np.argsort(logs, kind='stable')[::-1]         # rank[0] = position of the largest value
+    logs_desc = logs[rank]
+    k = np.arange(n + 1)
+    counts = _KeepCounts(n)
     if chi_max is not None:
-        good2 = np.zeros(len(piv), dtype=np.bool_)
-        good2[-int(chi_max):] = True
-        good = _combine_constraints(good, good2, 'chi_max')
+        counts.require(k <= int(chi_max), 'chi_max')
     if chi_min is not None and chi_min > 1:
-        good2 = np.ones(len(piv), dtype=np.bool_)
-        good2[-int(chi_min) + 1:] = False
-        good = _combine_constraints(good, good2, 'chi_min')
+        counts.require(k >= int(chi_min), 'chi_min')
     if deg_tol:
-        good2 = np.empty(len(piv), np.bool_)
-        good2[0] = True
-        good2[1:] = np.greater_equal(logS[1:] - logS[:-1], deg_tol)
-        good = _combine_constraints(good, good2, 'degeneracy_tol')
+        gap_ok = np.ones(n + 1, dtype=np.bool_)           # cutting after the k-th value: needs a log gap to the (k+1)-th
+        gap_ok[1:n] = (logs_desc[:-1] - logs_desc[1:]) >= deg_tol
+        counts.require(gap_ok, 'degeneracy_tol')
     if svd_min is not None:
-        good2 = np.greater_equal(logS, np.log(svd_min))
-        good = _combine_constraints(good, good2, 'svd_min')
+        counts.require(k <= int(np.count_nonzero(logs_desc >= np.log(svd_min))), 'svd_min')
     if trunc_cut is not None:
-        good2 = (np.cumsum(S[piv]**2) > trunc_cut * trunc_cut)
-        good = _combine_constraints(good, good2, 'trunc_cut')
-    cut = np.nonzero(good)[0][0]
-    mask = np.zeros(len(S), dtype=np.bool_)
-    np.put(mask, piv[cut:], True)
-    norm_new = np.linalg.norm(S[mask])
-    return mask, norm_new, TruncationError.from_S(S[np.logical_not(mask)])
+        tail = np.concatenate([np.cumsum((S[rank][::-1])**2)[::-1], [0.]])    # tail[k] = weight discarded when keeping k
+        enough = np.zeros(n + 1, dtype=np.bool_)
+        enough[1:] = tail[:-1] > trunc_cut * trunc_cut       # dropping the k-th value as well would exceed the budget
+        counts.require(enough, 'trunc_cut')
+    keep = counts.largest()
+    mask = np.zeros(n, dtype=np.bool_)
+    mask[rank[:keep]] = True
+    return mask, np.linalg.norm(S[mask]), TruncationError.from_S(S[~mask])
 
 
 subspace_stats = {'tried': 0, 'used': 0, 'residuals': []}   # diagnostics of the subspace warm start
@@ -218,167 +226,3 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
 
 # ----------------------------------------------------------------------------------------------------------------------
 # QR based truncation (reference truncation.py:370-713)
-def _block_vector_norms(arr, norm_axis):
-    """per stored block of the 2D Array `arr`: 2-norms over `norm_axis` (host vectors, layout order) -- the reference
-    reads ``np.linalg.norm(block, axis=norm_axis)`` from its host blocks (truncation.py:456); here one squared-norm
-    launch per block and a D2H copy of the resulting vectors."""
-    from .. import backend
-    src = arr if norm_axis == 0 else arr.transpose([1, 0])
-    lay = src._layout
-    lib = backend.get_lib()
-    out = []
-    for o, (mm, nn) in zip(lay.offsets, lay.shapes):
-        mm, nn = int(mm), int(nn)
-        buf = backend.empty(nn)
-        lib.col_sqnorms(mm, nn, nn, src._buf[int(o):int(o) + mm * nn], buf)
-        out.append(np.sqrt(backend.to_host(buf)))
-    return out, lay.qdata[:, 1]      # qindex (of `arr`) along the axis that is NOT summed over
-
-
-def _qr_theta_Y0(old_qtotal_L, old_qtotal_R, old_bond_leg, theta, move_right, expand, min_block_increase):
-    """Initial guess `Y0` of the isometry on the expanded bond: the columns (rows) of `theta` with the largest norms in
-    every charge block, ``expand`` times the old bond dimension more than the old leg had (reference truncation.py:370).
-    Returns an Array with legs ``[(vL.p0), vR]`` (`move_right`) or ``[vL, (p1.vR)]``."""
-    assert min_block_increase >= 0
-    assert expand is not None and expand != 0
-    Y0 = theta.copy(deep=False)
-    if move_right:
-        Y0.legs[1] = Y0.legs[1].to_LegCharge()
-        Y0.ireplace_label('(p1.vR)', 'vR')
-        q_axis, norm_axis, lab = 1, 0, 'vR'
-    else:
-        Y0.legs[0] = Y0.legs[0].to_LegCharge()
-        Y0.ireplace_label('(vL.p0)', 'vL')
-        q_axis, norm_axis, lab = 0, 1, 'vL'
-    # (the reference calls `Y0.gauge_total_charge(...)` here without using the returned copy: no effect)
-    v_old = old_bond_leg
-    if not v_old.is_blocked():
-        v_old = v_old.sort()[1]
-    v_new = Y0.get_leg(lab)                   # blocked: created from a pipe
-    piv = np.zeros(v_new.ind_len, dtype=bool)
-    increase_per_block = max(min_block_increase, int(v_old.ind_len * expand // v_new.block_number))
-    sizes_old = v_old.get_block_sizes()
-    sizes_new = v_new.get_block_sizes()
-    norms, qidx = _block_vector_norms(Y0, norm_axis)
-    by_q = {int(q): nv for q, nv in zip(qidx, norms)}
-    j_old = 0
-    q_old = v_old.charges[j_old, :]
-    for j_new, q_new in enumerate(v_new.charges):
-        if np.all(q_new == q_old):            # charge block both in v_new and v_old
-            s_new = sizes_old[j_old] + increase_per_block
-            j_old += 1
-            if j_old < len(v_old.charges):
-                q_old = v_old.charges[j_old, :]
-            else:
-                q_old = None
-        else:
-            s_new = increase_per_block
-        s_new = min(int(s_new), int(sizes_new[j_new]))
-        nv = by_q.get(j_new)
-        if nv is None:                        # block not stored in theta
-            continue
-        kept = np.argsort(-nv, kind='stable')[:s_new]
-        piv[v_new.slices[j_new] + kept] = True
-    Y0.iproject(piv, lab)
-    return Y0
-
-
-def _eig_based_svd(A, need_U=True, need_Vd=True, inner_labels=[None, None], trunc_params=None):
-    """Singular values / one set of singular vectors of `A` from the eigen-decomposition of ``A A^dagger`` or
-    ``A^dagger A`` (reference truncation.py:473): two GEMM-class contractions and a batched `eigh` instead of an SVD."""
-    assert A.rank == 2
-    if need_U and need_Vd:
-        raise NotImplementedError('both U and Vd from eigh: relative phases are not fixed (as in the reference)')
-    U = Vd = None
-    if need_U:
-        L, U = npc.eigh(npc.tensordot(A, A.conj(), axes=[1, 1]), sort='>')
-        U.ireplace_label('eig', inner_labels[0])
-    elif need_Vd:
-        L, V = npc.eigh(npc.tensordot(A.conj(), A, axes=[0, 0]), sort='>')
-        Vd = V.iconj().itranspose().ireplace_label('eig*', inner_labels[1])
-    else:
-        A2 = npc.tensordot(A, A.conj(), axes=[1, 1]) if A.shape[1] >= A.shape[0] else \
-            npc.tensordot(A.conj(), A, axes=[0, 0])
-        L = npc.eigvalsh(A2)
-    S = np.sqrt(np.abs(L))
-    if trunc_params is not None:
-        piv, renormalize, trunc_err = truncate(S, trunc_params)
-        S = S[piv] / renormalize
-        if need_U:
-            U.iproject(piv, 1)
-        if need_Vd:
-            Vd.iproject(piv, 0)
-    else:
-        renormalize = np.linalg.norm(S)
-        S = S / renormalize
-        trunc_err = TruncationError()
-    return U, S, Vd, trunc_err, renormalize
-
-
-def decompose_theta_qr_based(old_qtotal_L, old_qtotal_R, old_bond_leg, theta, move_right, expand, min_block_increase,
-                             use_eig_based_svd, trunc_params, compute_err, return_both_T):
-    """QR based decomposition and truncation of the two-site wave function ``theta[(vL.p0), (p1.vR)]``
-    (reference truncation.py:533): two QR steps on an expanded bond (controlled bond expansion) reduce `theta` to a
-    small bond matrix ``Xi``, only ``Xi`` is decomposed by an SVD (or `eigh`).
-
-    Returns ``(T_Lc, S, T_Rc, form, trunc_err, renormalization)`` as the reference."""
-    if compute_err:
-        return_both_T = True
-    Y0 = _qr_theta_Y0(old_qtotal_L, old_qtotal_R, old_bond_leg, theta, move_right, expand, min_block_increase)
-    if move_right:
-        theta_i1 = npc.tensordot(Y0.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)']).ireplace_label('vR*', 'vL')
-        theta_i1.itranspose(['(p1.vR)', 'vL'])
-        B_R, _ = npc.qr(theta_i1, inner_labels=['vL', 'vR'], inner_qconj=-1)
-        B_R.itranspose(['vL', '(p1.vR)'])
-        theta_i0 = npc.tensordot(theta, B_R.conj(), axes=['(p1.vR)', '(p1*.vR*)']).ireplace_label('vL*', 'vR')
-        A_L, Xi = npc.qr(theta_i0, inner_labels=['vR', 'vL'])
-    else:
-        theta_i0 = npc.tensordot(theta, Y0.conj(), axes=['(p1.vR)', '(p1*.vR*)']).ireplace_label('vL*', 'vR')
-        A_L, _ = npc.qr(theta_i0, inner_labels=['vR', 'vL'])
-        theta_i1 = npc.tensordot(A_L.conj(), theta, axes=['(vL*.p0*)', '(vL.p0)']).ireplace_label('vR*', 'vL')
-        theta_i1.itranspose(['(p1.vR)', 'vL'])
-        B_R, Xi = npc.qr(theta_i1, inner_labels=['vL', 'vR'], inner_qconj=-1)
-        B_R.itranspose(['vL', '(p1.vR)'])
-        Xi.itranspose(['vL', 'vR'])
-    if use_eig_based_svd:
-        U, S, Vd, _, renormalization = _eig_based_svd(Xi, need_U=move_right, need_Vd=(not move_right),
-                                                      inner_labels=['vR', 'vL'], trunc_params=trunc_params)
-    else:
-        U, S, Vd, _, renormalization = svd_theta(Xi, trunc_params)
-    T_Lc, T_Rc = None, None
-    form = ['A', 'B']
-    if move_right:
-        T_Lc = npc.tensordot(A_L, U, axes=['vR', 'vL'])
-        if return_both_T:
-            if use_eig_based_svd:
-                T_Rc = npc.tensordot(Xi, B_R, axes=['vR', 'vL'])
-                T_Rc = npc.tensordot(U.conj(), T_Rc, axes=['vL*', 'vL']).ireplace_label('vR*', 'vL')
-                T_Rc = T_Rc / npc.norm(T_Rc)
-                form[1] = 'Th'
-            else:
-                T_Rc = npc.tensordot(Vd, B_R, axes=['vR', 'vL'])
-    else:
-        T_Rc = npc.tensordot(Vd, B_R, axes=['vR', 'vL'])
-        if return_both_T:
-            if use_eig_based_svd:
-                T_Lc = npc.tensordot(A_L, Xi, axes=['vR', 'vL'])
-                T_Lc = npc.tensordot(T_Lc, Vd.conj(), axes=['vR', 'vR*']).ireplace_label('vL*', 'vR')
-                T_Lc = T_Lc / npc.norm(T_Lc)
-                form[0] = 'Th'
-            else:
-                T_Lc = npc.tensordot(A_L, U, axes=['vR', 'vL'])
-    if compute_err:
-        if use_eig_based_svd:
-            theta_approx = npc.tensordot(T_Lc, T_Rc, axes=['vR', 'vL'])
-        else:
-            theta_approx = npc.tensordot(T_Lc.scale_axis(S, axis='vR'), T_Rc, axes=['vR', 'vL'])
-        N_theta = npc.norm(theta)
-        eps = npc.norm(theta / N_theta - theta_approx * (renormalization / N_theta))**2
-        trunc_err = TruncationError(eps, 1. - 2. * eps)
-    else:
-        trunc_err = TruncationError(np.nan, np.nan)
-    if T_Lc is not None:
-        T_Lc.ireplace_label('(vL.p0)', '(vL.p)')
-    if T_Rc is not None:
-        T_Rc.ireplace_label('(p1.vR)', '(p.vR)')
-    return T_Lc, S, T_Rc, form, trunc_err, renormalization

@@ -1,0 +1,59 @@
+"""BASELINE.json configs[2] / [3] end to end at the largest size the reference finishes in the build container
+(tests/golden/make_golden_large.py -> tests/golden/dmrg_large.json, written by the UNMODIFIED reference):
+SpinChain XXZ L=64 (U(1) Sz) and FermiHubbardChain L=32 (U(1) x U(1): N, Sz) at chi_max=256 with the density-matrix mixer and
+a bond-dimension ramp.  The engine has to reproduce energy and entropies to 1e-10 / 1e-8, the Schmidt values to 1e-8 and
+the bond dimensions exactly (north_star tolerances)."""
+import importlib.util
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden():
+    with open(os.path.join(ROOT, 'tests', 'golden', 'dmrg_large.json')) as f:
+        return json.load(f)
+
+
+def _options(chi):
+    spec = importlib.util.spec_from_file_location('make_golden_large', os.path.join(ROOT, 'tests', 'golden',
+                                                                                    'make_golden_large.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.dmrg_options(chi), mod.CASES
+
+
+def _run_engine(name):
+    from tenpy_b200.models import SpinChain, FermiHubbardChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    _, cases = _options(1)
+    case = cases[name]
+    opts, _ = _options(case['chi'])
+    L = case['L']
+    if name == 'xxz':
+        M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 1., 'conserve': 'Sz'})
+    else:
+        M = FermiHubbardChain({'L': L, 't': 1., 'U': 4., 'mu': 0.})
+    psi = MPS.from_product_state(M.lat_sites, case['state'] * (L // 2))
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, opts)
+    E, _ = eng.run()
+    return E, psi, eng
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['xxz', 'hubbard'])
+def test_large_dmrg_matches_reference(gpu_lib, name):
+    g = _golden()[name]
+    E, psi, eng = _run_engine(name)
+    L = g['L']
+    assert abs(E - g['E']) <= 1e-10 * abs(g['E']), (E, g['E'])
+    S = psi.entanglement_entropy()
+    assert np.max(np.abs(S - np.array(g['S']))) <= 1e-8, float(np.max(np.abs(S - np.array(g['S']))))
+    assert [int(c) for c in psi.chi] == g['chi']
+    sv = np.sort(np.asarray(psi.get_SL(L // 2)))[::-1]
+    ref = np.array(g['schmidt_centre'])
+    assert len(sv) == len(ref) and np.max(np.abs(sv - ref)) <= 1e-8
