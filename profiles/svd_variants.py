@@ -49,12 +49,14 @@ def main():
                                                      (50, 50), (49, 50), (8, 8)])]
     for name, shapes in cases:
         row = {'case': name}
-        for v in (1, 3):
+        for v, inner in ((1, 2), (3, 2), (3, 1)):
             old = lib.svd_set_eig_variant(v)
+            old_in = lib.svd_set_eig_inner_sweeps(inner)
             ms, sweeps = run(lib, shapes, reps=2 if shapes[0][0] >= 2048 else 3)
             lib.svd_set_eig_variant(old)
-            row['v%d_ms' % v] = round(ms, 3)
-            row['v%d_sweeps' % v] = sweeps
+            lib.svd_set_eig_inner_sweeps(old_in)
+            row['v%d_in%d_ms' % (v, inner)] = round(ms, 3)
+            row['v%d_in%d_sweeps' % (v, inner)] = sweeps
         print(json.dumps(row))
         sys.stdout.flush()
 
