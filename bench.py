@@ -61,6 +61,9 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-blocksparse', action='store_true', help='skip the configs[2]/[3] shaped matvec probes')
+    ap.add_argument('--driver', default='own', choices=['own', 'reference'],
+                    help="'reference': the unmodified tenpy TwoSiteDMRGEngine (tenpy_b200.dropin) drives the sweep on the device "
+                         "engine instead of tenpy_b200.algorithms.dmrg (short line; the default run reports it as `reference_driver`)")
     ap.add_argument('--ref-budget-s', type=float, default=240., help='--impl reference: wall-clock budget of the measured steps')
     ap.add_argument('--scan', default='auto', choices=['auto', 'on', 'off'],
                     help='BASELINE.json configs[4]: chi in {256,512,1024,2048} x two fields, sharded over the ranks by LPT '
@@ -524,7 +527,7 @@ def run_b200(args):
     model = TFIChain({'L': L, 'J': J, 'g': g, 'conserve': None})
     psi = synthetic_mps(model, L, chi, d, seed=rank)
     opts = {'mixer': None, 'combine': True, 'diag_method': 'lanczos',      # as tests/benchmark/dmrg_infinite.py:9,44
-            'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None},
+            'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None, 'svd_deflation_tol': 1e-10},
             'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N},
             # cold-started SVD at every bond (the subspace warm start would only engage below the 1e-10 tolerance,
             # the Lanczos update of this workload changes theta by ~2e-7 per bond)
@@ -584,27 +587,6 @@ def run_b200(args):
         finally:
             eng.options.pop('identity_env', None)
 
-    # ---- the same state with the reference's DEFAULT Lanczos settings (N_min=2, N_max=20, convergence by P_tol): a converged
-    #      DMRG needs 2-3 matvecs per bond instead of the harness' fixed 10, so SVD / block moves / host latencies weigh more
-    default_lanczos = {}
-    try:
-        opts2 = dict(opts)
-        opts2['lanczos_params'] = {}
-        eng2 = dmrg.TwoSiteDMRGEngine(psi, model, opts2)
-        eng2.sweep()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        b0.record()
-        eng2.sweep()
-        b1.record()
-        torch.cuda.synchronize()
-        default_lanczos = {'sweep_s': b0.elapsed_time(b1) / 1e3,
-                           'N_lanczos_mean': float(np.mean(eng2.update_stats['N_lanczos'][-2 * (L - 2):])),
-                           'E': float(eng2.update_stats['E_total'][-1])}
-        del eng2
-    except Exception as e:   # never lose the bench line
-        default_lanczos = {'error': repr(e)}
-
     # ---- one more sweep with per-family CUDA-event profiling (after the timed one: same, converged regime; the
     #      event pairs bracket every library call, so host gaps inside a call -- the SVD reads q doubles per Jacobi
     #      sweep -- count for that family)
@@ -629,6 +611,27 @@ def run_b200(args):
         barrier()
         e2e = {'value': e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'note': 'MPS tensors from pinned host memory -> sweep (environments rebuilt) -> MPS back to host'}
+
+    # ---- the same state with the reference's DEFAULT Lanczos settings (N_min=2, N_max=20, convergence by P_tol): a converged
+    #      DMRG needs 2-3 matvecs per bond instead of the harness' fixed 10, so SVD / block moves / host latencies weigh more
+    default_lanczos = {}
+    try:
+        opts2 = dict(opts)
+        opts2['lanczos_params'] = {}
+        eng2 = dmrg.TwoSiteDMRGEngine(psi, model, opts2)
+        eng2.sweep()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        b0.record()
+        eng2.sweep()
+        b1.record()
+        torch.cuda.synchronize()
+        default_lanczos = {'sweep_s': b0.elapsed_time(b1) / 1e3,
+                           'N_lanczos_mean': float(np.mean(eng2.update_stats['N_lanczos'][-2 * (L - 2):])),
+                           'E': float(eng2.update_stats['E_total'][-1])}
+        del eng2
+    except Exception as e:   # never lose the bench line
+        default_lanczos = {'error': repr(e)}
 
     # ---- kernel roofline probes at the centre-bond shapes (CUDA events on the launching stream)
     roof = kernel_probes(lib, chi, d, D)
@@ -708,6 +711,14 @@ def run_b200(args):
                   'per_bond_s': est['per_bond_s'], 'matvec_gflops': est['matvec_gflops'],
                   'matvec_s': est['matvec_s'], 'matvec_split_s': est['matvec_split_s']}
         line['cpu_baseline'] = cb
+    if world == 1 and not args.no_e2e:
+        # the same sweep driven by the unmodified reference's engine class (own process)
+        try:
+            del eng, psi
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        line['reference_driver'] = reference_driver_line(args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -732,7 +743,7 @@ def run_chi_scan(args, lib, world, rank):
         model = TFIChain({'L': args.L, 'J': 1., 'g': cfg['g'], 'conserve': None})
         psi = synthetic_mps(model, args.L, cfg['chi'], 2, seed=cfg['chi'])
         opts = {'mixer': None, 'combine': True, 'diag_method': 'lanczos', 'svd_warm_start': False,
-                'trunc_params': {'chi_max': cfg['chi'], 'svd_min': 1e-45, 'trunc_cut': None},
+                'trunc_params': {'chi_max': cfg['chi'], 'svd_min': 1e-45, 'trunc_cut': None, 'svd_deflation_tol': 1e-10},
                 'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N}}
         eng = dmrg.TwoSiteDMRGEngine(psi, model, opts)
         eng.sweep()
@@ -973,10 +984,76 @@ def kernel_probes(lib, chi, d, D):
     return {'gemm': gemm, 'svd': svdr}
 
 
+def run_b200_reference_driver(args):
+    """The benchmark sweep driven by the UNMODIFIED reference: ``tenpy.algorithms.dmrg.TwoSiteDMRGEngine.sweep`` (its
+    `Sweep` loop, `update_local`, `mixed_svd` -> `svd_theta` / `truncate`, `LanczosGroundState`, `MPOEnvironment`, `MPS`,
+    `TFIChain`) on the device engine through `tenpy_b200.dropin`; the effective Hamiltonian is the engine's device-optimised
+    `TwoSiteH` plugged in at the reference's `EffectiveH` hook.  Same synthetic state and options as the default arm."""
+    import torch
+    from tenpy_b200 import backend, dropin
+    from tenpy_b200._lib import DeviceLib
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    lib = backend.use_library(DeviceLib())
+    path = dropin.install()
+    if path is None:
+        print(json.dumps({'driver': 'reference', 'unavailable': 'no reference install (baseline/_ref)'}))
+        return
+    import tenpy
+    from tenpy.models.tf_ising import TFIChain
+    from tenpy.networks.mps import MPS
+    import tenpy.linalg.np_conserved as npc
+    L, chi, d = args.L, args.chi, 2
+    M = TFIChain({'L': L, 'J': 1., 'g': 1., 'bc_MPS': 'finite', 'conserve': None})
+    sites = M.lat.mps_sites()
+
+    class _Shim:                      # synthetic_mps only needs the site legs
+        lat_sites = sites
+    own = synthetic_mps(_Shim, L, chi, d, seed=0)
+    psi = MPS(sites, [B for B in own._B], [np.asarray(s_) for s_ in own._S], bc='finite', form='B')
+    opts = {'mixer': None, 'combine': True, 'diag_method': 'lanczos',
+            'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None, 'svd_deflation_tol': 1e-10},
+            'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N}}
+    opts['trunc_params'].pop('svd_deflation_tol')        # not an option of the reference's svd_theta ...
+    npc.SVD_DEFAULTS['deflation_tol'] = 1e-10             # ... the engine's npc.svd takes it as its default instead
+    Engine = dropin.fast_two_site_engine()
+    eng = Engine(psi, M, opts)
+    for _ in range(args.warmup):
+        eng.sweep()
+    torch.cuda.synchronize()
+    lib.kernel_launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        eng.sweep()
+    ev1.record()
+    torch.cuda.synchronize()
+    E = float(eng.update_stats['E_total'][-1])
+    E_exact = exact_tfi_energy(L, 1., 1.)
+    print(json.dumps({'driver': 'reference', 'impl': 'b200', 'metric': METRIC, 'unit': UNIT,
+                      'value': ev0.elapsed_time(ev1) / 1e3 / args.steps, 'steps': args.steps, 'warmup': args.warmup,
+                      'gpu_launches': int(lib.kernel_launch_count()), 'E': E, 'E_rel_err': abs(E - E_exact) / abs(E_exact),
+                      'engine_module': npc.__name__, 'dmrg_file': tenpy.algorithms.dmrg.__file__,
+                      'int8_products': npc.OZAKI['calls']}))
+
+
+def reference_driver_line(args):
+    """run `--driver reference` in its own process (the engine has to be seeded before `import tenpy`) and return its line"""
+    cmd = [sys.executable, os.path.abspath(__file__), '--driver', 'reference', '--steps', '1', '--warmup', '2', '--L', str(args.L),
+           '--chi', str(args.chi), '--lanczos-N', str(args.lanczos_N)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, WORLD_SIZE='1', RANK='0'))
+        lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+        return json.loads(lines[-1]) if lines else {'error': out.stderr[-500:]}
+    except Exception as e:
+        return {'error': repr(e)}
+
+
 def main():
     args = parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.driver == 'reference':
+        run_b200_reference_driver(args)
     else:
         run_b200(args)
 

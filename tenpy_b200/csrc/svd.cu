@@ -687,8 +687,10 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- host driver -----------------------------------------------------------------------------------
-static int g_eig_variant = 1;   // pivot eigen-solver: 1 = jacobi_eig_kernel (shared memory), 3 = jacobi_eig_kernel_v3 (registers + shuffles)
-static int g_eig_inner_sweeps = J_INNER_SWEEPS;   // inner sweeps of version 3 (version 1: fixed J_INNER_SWEEPS)
+// pivot eigen-solver: 3 = jacobi_eig_kernel_v3 (registers + shuffles; default since r02g: generic 2048^2 block 175 -> 145 ms,
+// XXZ-shaped block set 44 -> 32 ms with one inner sweep), 1 = jacobi_eig_kernel (shared memory, two inner sweeps)
+static int g_eig_variant = 3;
+static int g_eig_inner_sweeps = 1;   // inner sweeps of version 3 (version 1: fixed J_INNER_SWEEPS)
 struct JLayout {
     std::vector<JMat> mats;
     std::vector<int> cta_mat;

@@ -1391,6 +1391,12 @@ def _guess_is_orthogonal_basis(G, leg, axis_keep, a_qind):
     return all(q in have for q in set(a_qind.tolist()))
 
 
+# `deflation_tol` used by `svd` when the caller passes none: callers that cannot pass the extension argument (the
+# reference's own `svd_theta` running on this engine, tenpy_b200.dropin) set it here
+SVD_DEFAULTS = {'deflation_tol': None}
+_SVD_LIB_STATE = object()      # internal: "the tolerance is already set in the library"
+
+
 def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, None], inner_labels=[None, None],
         inner_qconj=+1, guess=None, deflation_tol=None, n_keep=None):
     """Singular value decomposition ``a = U diag(S) VH`` of a 2D Array (reference npc:3676).
@@ -1407,11 +1413,14 @@ def svd(a, full_matrices=False, compute_uv=True, cutoff=None, qtotal_LR=[None, N
     keeps the library default (rounding level only, LAPACK-grade factorisation).
     `n_keep` (extension, optional): the caller keeps at most that many singular triplets (``chi_max``); vectors of
     negligible directions beyond it are not completed (they are zero, their `S` is exactly 0)."""
-    if deflation_tol is not None:
+    if deflation_tol is None:
+        deflation_tol = SVD_DEFAULTS['deflation_tol']        # module-wide default (None: rounding level only)
+    if deflation_tol is not None and deflation_tol is not _SVD_LIB_STATE:
         lib0 = backend.get_lib()
         old_tol = lib0.svd_set_deflation_tol(deflation_tol)
         try:
-            return svd(a, full_matrices, compute_uv, cutoff, qtotal_LR, inner_labels, inner_qconj, guess, None, n_keep)
+            return svd(a, full_matrices, compute_uv, cutoff, qtotal_LR, inner_labels, inner_qconj, guess, _SVD_LIB_STATE,
+                       n_keep)
         finally:
             lib0.svd_set_deflation_tol(old_tol)
     if guess is not None and compute_uv and cutoff is None and not full_matrices and a.rank == 2:

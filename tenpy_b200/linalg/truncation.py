@@ -187,16 +187,22 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
 
     Returns ``(U, S, VH, err, renormalization)`` with ``theta ~= U diag(S * renormalization) VH``.
     Extensions (all optional, the defaults reproduce the reference's behaviour up to the deflation tolerance):
-    ``trunc_par['svd_deflation_tol']`` (default 1e-10): singular directions below that fraction of ``|theta|``
-    are not iterated to convergence inside the Jacobi SVD -- their values are reported approximately
-    (absolute error below the tolerance) and their vectors are an orthonormal completion; the state changes by
-    at most that relative amount, the energy to second order in it.
+    ``trunc_par['svd_deflation_tol']``: singular directions below that fraction of ``|theta|`` are not iterated to
+    convergence inside the Jacobi SVD -- their values are reported approximately (absolute error below the tolerance) and
+    their vectors are an orthonormal completion; the state changes by at most that relative amount, the energy to second
+    order in it.  Default: ``min(1e-10, svd_min)`` -- never above the smallest Schmidt value the truncation may keep, so
+    that every KEPT value is a converged singular value (with ``svd_min=None`` or 0: the rounding-level deflation of
+    `npc.svd` only).  A caller that keeps values below 1e-10 on purpose (the benchmark harness: ``svd_min=1e-45`` to hold
+    chi saturated) passes the tolerance explicitly.
     `subspace` = ``(U_k, VH_k)``, the truncated isometries kept at this bond by the previous update: see
     :func:`_subspace_svd` (used only if the part of `theta` outside their span is below the same tolerance; its
     weight is added to the truncation error).
     `guess` is handed to :func:`npc.svd` (complete orthonormal bases, warm start); if `full_out` is a list the
     untruncated ``(U, VH)`` are appended to it."""
-    tol = trunc_par.get('svd_deflation_tol', 1.e-10)
+    tol = trunc_par.get('svd_deflation_tol', None)
+    if tol is None:
+        svd_min = trunc_par.get('svd_min', 1.e-14)
+        tol = min(1.e-10, svd_min) if svd_min else 0.
     chi_max = trunc_par.get('chi_max', 100)
     res = _subspace_svd(theta, subspace, tol, chi_max, qtotal_LR, inner_labels) if subspace is not None else None
     lost = 0.
@@ -222,7 +228,3 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
     U.iproject(piv, axes=1)
     VH.iproject(piv, axes=0)
     return U, S, VH, err, renormalization
-
-
-# ----------------------------------------------------------------------------------------------------------------------
-# QR based truncation (reference truncation.py:370-713)
