@@ -61,6 +61,11 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-blocksparse', action='store_true', help='skip the configs[2]/[3] shaped matvec probes')
+    ap.add_argument('--workload', default='tfi', choices=['tfi', 'xxz', 'hubbard'],
+                    help='tfi = BASELINE.json configs[1] (the metric; default).  xxz / hubbard = configs[2] / [3] end to end: '
+                         'SpinChain L=100 chi=1024 (U(1) Sz) / FermiHubbardChain L=64 chi=2048 (U(1)xU(1)): chi ramp with the '
+                         'density-matrix mixer, then timed sweeps (own line, not the contract metric)')
+    ap.add_argument('--ramp', type=int, default=6, help='--workload xxz|hubbard: sweeps of the chi ramp (doubling from 32)')
     ap.add_argument('--driver', default='own', choices=['own', 'reference'],
                     help="'reference': the unmodified tenpy TwoSiteDMRGEngine (tenpy_b200.dropin) drives the sweep on the device "
                          "engine instead of tenpy_b200.algorithms.dmrg (short line; the default run reports it as `reference_driver`)")
@@ -1048,8 +1053,109 @@ def reference_driver_line(args):
         return {'error': repr(e)}
 
 
+def run_blocksparse(args):
+    """BASELINE.json configs[2] / [3] end to end on one GPU: two-site DMRG with charge conservation from a product state,
+    bond dimension ramped up (mixer on), then `--steps` timed sweeps at the final chi (mixer off, the reference's default
+    adaptive Lanczos).  One JSON line: seconds per sweep, kernel-family times, the contraction-size histogram (where the
+    GEMM time goes), sector / block structure, E, S.  Parity of this path: tests/test_large_parity.py (same models at
+    L=64 / L=32, chi=256 against the unmodified reference)."""
+    import torch
+    from tenpy_b200 import backend
+    from tenpy_b200._lib import DeviceLib
+    from tenpy_b200.models import SpinChain, FermiHubbardChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    from tenpy_b200.linalg import np_conserved as npc
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    lib = backend.use_library(DeviceLib())
+    xxz = args.workload == 'xxz'
+    L = args.L if args.L != 100 or xxz else 64
+    chi = args.chi if args.chi != 1024 or xxz else 2048
+    M = SpinChain({'L': L, 'Jx': 1., 'Jy': 1., 'Jz': 1., 'conserve': 'Sz'}) if xxz else \
+        FermiHubbardChain({'L': L, 't': 1., 'U': 4., 'mu': 0.})
+    psi = MPS.from_product_state(M.lat_sites, ['up', 'down'] * (L // 2))
+    chis = [min(chi, 32 * 2**k) for k in range(args.ramp)]
+    chis[-1] = chi
+    opts = {'mixer': True, 'mixer_params': {'amplitude': 1e-4, 'decay': 2., 'disable_after': args.ramp},
+            'combine': True, 'trunc_params': {'chi_max': chis[0], 'svd_min': 1e-12}}
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, opts)
+    t_ramp = []
+    for c in chis:
+        eng.trunc_params['chi_max'] = c
+        t0 = time.perf_counter()
+        eng.sweep()
+        lib.synchronize()
+        t_ramp.append(round(time.perf_counter() - t0, 3))
+    eng.mixer_deactivate()
+    for _ in range(args.warmup):
+        eng.sweep()
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    lib.kernel_launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        eng.sweep()
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = lib.kernel_launch_count()
+    sweep_s = ev0.elapsed_time(ev1) / 1e3 / args.steps
+    clocks = sampler.summary()
+    # one more sweep with per-call profiling
+    lib.profile = {}
+    plans0 = len(npc._PLAN_CACHE)
+    t0 = time.perf_counter()
+    eng.sweep()
+    lib.synchronize()
+    wall = time.perf_counter() - t0
+    fam = {k: round(v[1], 1) for k, v in lib.profile_summary().items()}
+    det = lib.profile_detail()
+    lib.profile = None
+    g = [(ms, info) for ms, info in det.get('gemm', []) if info]
+    hist = []
+    for lo, hi in ((0, 1e6), (1e6, 1e7), (1e7, 1e8), (1e8, 1e9), (1e9, 1e10), (1e10, 1e13)):
+        sel = [(ms, i) for ms, i in g if lo <= i[0] < hi]
+        if sel:
+            tms, tfl = sum(x[0] for x in sel), sum(x[1][0] for x in sel)
+            hist.append({'flop_range': [lo, hi], 'calls': len(sel), 'ms': round(tms, 2), 'gflop': round(tfl / 1e9, 2),
+                         'tflops': round(tfl / tms / 1e9, 3) if tms else None})
+    i0 = L // 2 - 1
+    H = TwoSiteH(eng.env, i0, combine=True)
+    theta = H.combine_theta(psi.get_theta(i0, 2))
+    nb = 2 * (L - 2)
+    peaks, peaks_kind = measured_peaks()
+    total_flop = float(sum(i[0] for _, i in g))
+    line = {'metric': METRIC, 'value': sweep_s, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': sweep_s * 1e3, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'product state -> DMRG (no synthetic tensors)', 'impl': 'b200',
+            'config': {'workload': ('SpinChain XXZ L=%d chi=%d, U(1) Sz' if xxz else 'FermiHubbardChain L=%d chi=%d, U(1)xU(1) (N, Sz)')
+                       % (L, chi) + ', two-site DMRG sweep after a chi ramp %r with the density-matrix mixer; timed sweeps: mixer '
+                       'off, adaptive Lanczos (reference defaults), svd_min=1e-12' % (chis,), 'L': L, 'chi': chi,
+                       'l2': 'working set (environments + MPS) >> 126 MB L2'},
+            'clocks': clocks, 'gpu_launches': int(launches), 'ramp_sweep_s': t_ramp, 'chi_reached': int(max(psi.chi)),
+            'result': {'E': float(eng.update_stats['E_total'][-1]), 'S_mid': float(psi.entanglement_entropy()[L // 2 - 1]),
+                       'N_lanczos_mean': float(np.mean(eng.update_stats['N_lanczos'][-nb:])),
+                       'trunc_err_max': float(max(getattr(e, 'eps', e) for e in eng.update_stats['err'][-nb:]))},
+            'structure': {'theta_blocks': int(theta.stored_blocks), 'theta_shape': list(theta.shape),
+                          'theta_largest_block': [int(x) for x in theta._layout.shapes[np.argmax(theta._layout.sizes)]],
+                          'bond_sectors': int(psi.get_B(L // 2).get_leg('vL').block_number)},
+            'kernel_family_ms_per_sweep': fam, 'host_wall_s_profiled_sweep': wall,
+            'gemm_by_flops': hist, 'plans_built_profiled_sweep': len(npc._PLAN_CACHE) - plans0,
+            'contraction_flop_per_sweep': total_flop,
+            'roofline': {'bound': 'tensor', 'achieved': total_flop / max(fam.get('gemm', 0.), 1e-9) / 1e9, 'peak': FP64_TENSOR_PEAK_TFLOPS,
+                         'unit': 'TFLOP/s', 'frac': total_flop / max(fam.get('gemm', 0.), 1e-9) / 1e9 / FP64_TENSOR_PEAK_TFLOPS,
+                         'traffic': None, 'kernel': 'grouped_gemm_kernel / thin_n / thin_m / oz_gemm_kernel (all contractions of a sweep)',
+                         'note': 'ragged charge blocks: launch / latency bound, see gemm_by_flops'},
+            'peaks': peaks_kind}
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
+    if args.workload != 'tfi' and args.impl != 'reference':
+        return run_blocksparse(args)
     if args.impl == 'reference':
         run_reference(args)
     elif args.driver == 'reference':

@@ -299,12 +299,18 @@ class TwoSiteH:
         self._LP_rest._oz_const = self._RP_rest._oz_const = True
         self._leg_IdL = LP_one.get_leg('wR')     # unit legs carrying the charge of the identity component
         self._leg_IdR = RP_one.get_leg('wL')
-        if self._W01 is None:
-            self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])
-        W_rest, W_one = pieces(self._W01, 'wL', only_l)
-        W01p = npc.concatenate([W_rest, W_one], axis='wL')                   # wL: [others ..., IdL]
-        W_rest, W_one = pieces(W01p, 'wR', only_r)
-        self._W01p = npc.concatenate([W_rest, W_one], axis='wR')             # wR: [others ..., IdR]
+        # everything below depends on the MPO and the bond only (not on the state): made once per bond, kept on the MPO
+        cache = H.__dict__.setdefault('_b200_two_site_cache', {})
+        ent = cache.get(self.i0)
+        if ent is None:
+            if self._W01 is None:
+                self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])
+            W_rest, W_one = pieces(self._W01, 'wL', only_l)
+            W01p = npc.concatenate([W_rest, W_one], axis='wL')                   # wL: [others ..., IdL]
+            W_rest, W_one = pieces(W01p, 'wR', only_r)
+            ent = cache[self.i0] = {'W01': self._W01, 'W01p': npc.concatenate([W_rest, W_one], axis='wR')}   # wR: [others ..., IdR]
+        self._W01, self._W01p = ent['W01'], ent['W01p']
+        self._mpo_cache = ent
         self._mask_rest_r = np.arange(D_r) < D_r - 1
         return True
 
@@ -453,9 +459,14 @@ class TwoSiteH:
         K1, K2 = Dm1 * d0 * d1, d0 * d1
         if K1 + K2 > 32:
             return None
+        ent = getattr(self, '_mpo_cache', None)
+        if getattr(self, '_M_id', None) is None and ent is not None and 'M_id' in ent:
+            self._M_id, self._N1, self._fused_legs = ent['M_id'], ent['N1'], ent['fused_legs']
+            self._RP_rest_t = self._RP_rest.transpose(['wL', 'vL', 'vL*'])
+            self._RP_rest_t._oz_const = True
         if getattr(self, '_M_id', None) is None:
             # (W0 W1) as a matrix [(p0' p1' wR), (wL p0 p1)] with the identity components moved to the end of both
-            # index groups; D^2 d^4 model constants, permuted on the host once per bond
+            # index groups; D^2 d^4 model constants, permuted on the host once per bond (and kept on the MPO)
             H = self._H_mpo
             IdL, IdR = H.get_IdL(self.i0), H.get_IdR(self.i0 + 1)
             W = self._W01.transpose(['p0', 'p1', 'wR', 'wL', 'p0*', 'p1*']).to_ndarray()
@@ -471,6 +482,8 @@ class TwoSiteH:
             self._RP_rest_t._oz_const = True
             self._N1 = d0 * d1 * len(rest_r)
             self._fused_legs = (self._W01.get_leg('p0'), self._W01.get_leg('p1'), self._RP_rest.get_leg('wL').conj())
+            if ent is not None:
+                ent.update({'M_id': self._M_id, 'N1': self._N1, 'fused_legs': self._fused_legs})
         N1, N2 = self._N1, K2
         p0leg, p1leg, wleg = self._fused_legs
         legs_r = [t1.legs[0], p0leg, p1leg, wleg, t1.legs[4]]

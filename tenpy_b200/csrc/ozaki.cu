@@ -21,8 +21,9 @@
 //
 // Kernel (persistent, one CTA per SM, 8 warps): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
 // allocation, warps 4..7 = epilogue (TMEM -> registers -> FP64 -> C).  512 TMEM columns = 4 int32 accumulators of
-// 128 x 128, so the diagonals are processed in passes of 4 (least significant pass first); within a pass every loaded
-// slice tile is reused by up to 4 MMAs.
+// 128 x 128, so the diagonals are processed in passes of up to 4, least significant pass first and the groups aligned at the
+// top (s = 7: d = 3..6 then d = 0..2): the last pass needs the fewest slices; within a pass every loaded slice tile is
+// reused by up to 4 MMAs.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             const int mt = tile % mt_count, nt = tile / mt_count;
             for (int g = npass - 1; g >= 0 && ok; --g) {
-                const int nsl = min(s, 4 * g + 4);                   // slices 0 .. nsl-1 of both operands are needed
+                const int nsl = s - 4 * (npass - 1 - g);             // slices 0 .. nsl-1 of both operands are needed (= d_hi + 1)
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int slot = it % nst;
                     const long long tw = clock64();
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         long long t_full = 0, t_acc = 0, t0 = clock64();
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
-                const int d_lo = 4 * g, d_hi = min(4 * g + 3, s - 1);
+                const int d_hi = s - 1 - 4 * (npass - 1 - g), d_lo = max(0, d_hi - 3);
                 long long tw = clock64();
                 ok = mbar_wait(&acc_empty, (pass_it & 1) ^ 1, p.abort_flag);   // epilogue has drained the accumulators
                 t_acc += clock64() - tw;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
             const int mt = tile % mt_count, nt = tile / mt_count;
             const double *sbp = p.sB + (int64_t)nt * OZ_TILE;
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
-                const int d_lo = 4 * g, d_hi = min(4 * g + 3, s - 1);
+                const int d_hi = s - 1 - 4 * (npass - 1 - g), d_lo = max(0, d_hi - 3);
                 const long long tw = clock64();
                 ok = mbar_wait(&acc_full, pass_it & 1, p.abort_flag);
                 t_wait += clock64() - tw;
@@ -286,64 +287,59 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                 // weight of the pass: 2^(-12 - 7 d_lo)
                 const double wpass = __longlong_as_double((long long)(1023 - 12 - 7 * d_lo) << 52);
                 const bool add = (g != npass - 1) || p.accumulate;
-                // Accumulators are read with the 16x256b fragment shape: a thread holds two columns of two rows per 8-column
-                // group, four threads cover 64 contiguous bytes of a C row -> every global access is sector-complete and no
-                // transposition is needed (the 32x32b shape gives a thread 32 columns of ONE row: 32 scattered words per
-                // access; an in-register transposition fixed that at ~160 shuffles per 32 x 32 chunk, r02f).
-                const bool vec = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int ra = mt * OZ_TILE + q * 32 + hh * 16 + (lane >> 2), rb = ra + 8;
-                    const double sa_a = p.sA[ra] * wpass, sa_b = p.sA[rb] * wpass;    // sA is padded to whole tiles
-                    const uint32_t tl = tmem + ((uint32_t)(q * 32 + hh * 16) << 16);
-#pragma unroll 1
-                    for (int c0 = 0; c0 < OZ_TILE; c0 += 32) {
-                        double h[16];
-                        uint32_t r[16];
-                        tmem_ld_16x256b_x4(tl + (uint32_t)(d_hi - d_lo) * OZ_TILE + c0, r);
+                const int row0 = mt * OZ_TILE + q * 32;                // the 32 rows of this warp
+                const double sa_l = p.sA[row0 + lane];                 // scale of this lane's row (sA is padded to whole tiles)
+                for (int c0 = 0; c0 < OZ_TILE; c0 += 32) {
+                    double h[32];
+                    uint32_t r[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d_hi - d_lo) * OZ_TILE + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        h[j] = __hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0;
+                    for (int d = d_hi - 1; d >= d_lo; --d) {
+                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d - d_lo) * OZ_TILE + c0, r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            h[j] = __hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0;
-                        for (int d = d_hi - 1; d >= d_lo; --d) {
-                            tmem_ld_16x256b_x4(tl + (uint32_t)(d - d_lo) * OZ_TILE + c0, r);
-                            tmem_ld_wait();
+                        for (int j = 0; j < 32; ++j)
+                            h[j] = fma(h[j], 0.0078125,
+                                       __hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0);
+                    }
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                h[j] = fma(h[j], 0.0078125,
-                                           __hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0);
-                        }
+                    for (int j = 0; j < 32; ++j) h[j] *= sa_l;          // row scale 2^ea_i while lane = row
+                    // (A/B on the B200, r02h: reading the accumulators with the 16x256b fragment shape instead -- 64-byte row
+                    // segments per four threads, no transposition -- made the epilogue 2x SLOWER, 0.339 vs 0.268 ms per
+                    // 2048 x 4096 x 1024 product; this version stays.)
+                    // lane = row, register = column  ->  lane = column, register = row (butterfly transposition with
+                    // static register indices), so that every global access of the warp is one contiguous 256-byte row
+                    // segment of C instead of 32 scattered 8-byte words
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            const int cl = c0 + 8 * g8 + 2 * (lane & 3);          // column inside the tile (even)
-                            const int col = nt * OZ_TILE + cl;
-                            const double sb0 = sbp[cl], sb1 = sbp[cl + 1];       // sB is padded to whole tiles
-                            double va0 = h[4 * g8 + 0] * sa_a * sb0, va1 = h[4 * g8 + 1] * sa_a * sb1;
-                            double vb0 = h[4 * g8 + 2] * sa_b * sb0, vb1 = h[4 * g8 + 3] * sa_b * sb1;
-                            double *pa = p.C + (int64_t)ra * p.ldc + col, *pb = p.C + (int64_t)rb * p.ldc + col;
-                            if (vec && col + 1 < p.N) {
-                                if (ra < p.M) {
-                                    if (add) {
-                                        const double2 o = *reinterpret_cast<const double2 *>(pa);
-                                        va0 += o.x;
-                                        va1 += o.y;
-                                    }
-                                    *reinterpret_cast<double2 *>(pa) = make_double2(va0, va1);
-                                }
-                                if (rb < p.M) {
-                                    if (add) {
-                                        const double2 o = *reinterpret_cast<const double2 *>(pb);
-                                        vb0 += o.x;
-                                        vb1 += o.y;
-                                    }
-                                    *reinterpret_cast<double2 *>(pb) = make_double2(vb0, vb1);
-                                }
-                            } else {
-                                if (ra < p.M && col < p.N) pa[0] = add ? va0 + pa[0] : va0;
-                                if (ra < p.M && col + 1 < p.N) pa[1] = add ? va1 + pa[1] : va1;
-                                if (rb < p.M && col < p.N) pb[0] = add ? vb0 + pb[0] : vb0;
-                                if (rb < p.M && col + 1 < p.N) pb[1] = add ? vb1 + pb[1] : vb1;
+                    for (int b = 16; b >= 1; b >>= 1) {
+                        const bool up = (lane & b) != 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if ((j & b) == 0) {
+                                const double give = up ? h[j] : h[j | b];
+                                const double got = __shfl_xor_sync(0xffffffffu, give, b);
+                                if (up) h[j] = got; else h[j | b] = got;
                             }
+                        }
+                    }
+                    const int col = nt * OZ_TILE + c0 + lane;
+                    const double wsb = wpass * sbp[c0 + lane];         // sB is padded to whole tiles
+                    double *cp = p.C + (int64_t)row0 * p.ldc + col;
+                    if (col < p.N) {
+                        if (add) {
+                            double old[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) old[j] = (row0 + j < p.M) ? cp[(int64_t)j * p.ldc] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (row0 + j < p.M) cp[(int64_t)j * p.ldc] = fma(h[j], wsb, old[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (row0 + j < p.M) cp[(int64_t)j * p.ldc] = h[j] * wsb;
                         }
                     }
                 }

@@ -687,10 +687,12 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- host driver -----------------------------------------------------------------------------------
-// pivot eigen-solver: 3 = jacobi_eig_kernel_v3 (registers + shuffles; default since r02g: generic 2048^2 block 175 -> 145 ms,
-// XXZ-shaped block set 44 -> 32 ms with one inner sweep), 1 = jacobi_eig_kernel (shared memory, two inner sweeps)
+// pivot eigen-solver: 3 = jacobi_eig_kernel_v3 (registers + shuffles, default), 1 = jacobi_eig_kernel (shared memory).
+// Inner sweeps: ONE inner sweep is faster for generic full-rank blocks (2048^2: 176 -> 145 ms, XXZ-shaped set 40 -> 32 ms,
+// profiles/r02/r02g_svd_variants.jsonl) but the numerically low-rank two-site wave functions of a converged DMRG then
+// need 14 instead of 11 outer sweeps (svd family of the benchmark sweep 718 -> 819 ms, r02h): the default stays 2.
 static int g_eig_variant = 3;
-static int g_eig_inner_sweeps = 1;   // inner sweeps of version 3 (version 1: fixed J_INNER_SWEEPS)
+static int g_eig_inner_sweeps = J_INNER_SWEEPS;   // inner sweeps of version 3 (version 1: fixed J_INNER_SWEEPS)
 struct JLayout {
     std::vector<JMat> mats;
     std::vector<int> cta_mat;

@@ -144,19 +144,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
-// warp-collective, shape 16x256b repeated 4 times along the columns: 16 TMEM lanes (lane field of taddr: multiple of 16) x 32
-// columns.  Fragment layout (the mma.m16n8 accumulator layout per 8-column group g; verified on the B200 by
-// profiles/tc_i8_probe.cu `ldshape`): thread t holds  r[4g+0], r[4g+1] = row t/4,     columns 8g + 2(t%4) + {0, 1}
-//                                                      r[4g+2], r[4g+3] = row t/4 + 8, same columns.
-// Four threads cover 8 consecutive columns of a row: global accesses from this layout are 64-byte row segments.
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // byte offset of element (row r, k-byte kb) inside a 128-byte-swizzled K-major tile (rows of 128 bytes)

@@ -41,6 +41,9 @@ def main():
         def profile_summary(self):
             return {'gemm': (1, 1.0), 'svd': (1, 0.5)}
 
+        def profile_detail(self):
+            return {'gemm': [(1.0, (2.e6, 3, 2))], 'svd': [(0.5, None)]}
+
         def kernel_launch_count(self, reset=False):
             return 1
 

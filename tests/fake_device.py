@@ -63,8 +63,10 @@ def ozaki_product(a, b):
     """A . B^T from two `_FakeSplit` operands (rows of b = columns of the product)"""
     slices = a.digits.shape[0]
     C = np.zeros((a.digits.shape[1], b.digits.shape[1]))
-    for g in range((slices + 3) // 4 - 1, -1, -1):
-        d_lo, d_hi = 4 * g, min(4 * g + 3, slices - 1)
+    npass = (slices + 3) // 4
+    for g in range(npass - 1, -1, -1):
+        d_hi = slices - 1 - 4 * (npass - 1 - g)
+        d_lo = max(0, d_hi - 3)
         h = None
         for d in range(d_hi, d_lo - 1, -1):
             Cd = sum(a.digits[t] @ b.digits[d - t].T for t in range(d + 1))

@@ -43,3 +43,14 @@ def test_bench_reference_arm():
     if d['cpu_baseline']['kind'] == 'reference':
         assert d['cpu_baseline']['thread_sweep'] and d['cpu_baseline']['cores'] >= 1
     assert abs(d['value'] - d['per_bond_s'] * d['full_chi_bonds']) < 1e-9 * d['value']
+
+
+def test_bench_blocksparse_workload_dry_run():
+    """`--workload xxz` (BASELINE.json configs[2] end to end: chi ramp with the mixer, timed sweeps) on the test double"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'dev_bench_dryrun.py'), '--workload', 'xxz', '--L', '10',
+                          '--chi', '16', '--steps', '1', '--warmup', '0', '--ramp', '2'], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    assert d['config']['chi'] == 16 and 'XXZ' in d['config']['workload'] and d['value'] > 0
+    assert d['structure']['theta_blocks'] >= 2 and d['chi_reached'] <= 16 and 'gemm_by_flops' in d
