@@ -65,6 +65,9 @@ def parse_args():
                     help='tfi = BASELINE.json configs[1] (the metric; default).  xxz / hubbard = configs[2] / [3] end to end: '
                          'SpinChain L=100 chi=1024 (U(1) Sz) / FermiHubbardChain L=64 chi=2048 (U(1)xU(1)): chi ramp with the '
                          'density-matrix mixer, then timed sweeps (own line, not the contract metric)')
+    ap.add_argument('--svd-warm-start', default='default', choices=['default', 'off', 'subspace', 'full'],
+                    help='--workload xxz|hubbard: engine option svd_warm_start (default: the engine default)')
+    ap.add_argument('--svd-min', type=float, default=1e-10, help='--workload xxz|hubbard: truncation threshold svd_min')
     ap.add_argument('--ramp', type=int, default=6, help='--workload xxz|hubbard: sweeps of the chi ramp (doubling from 32)')
     ap.add_argument('--driver', default='own', choices=['own', 'reference'],
                     help="'reference': the unmodified tenpy TwoSiteDMRGEngine (tenpy_b200.dropin) drives the sweep on the device "
@@ -1078,7 +1081,9 @@ def run_blocksparse(args):
     chis = [min(chi, 32 * 2**k) for k in range(args.ramp)]
     chis[-1] = chi
     opts = {'mixer': True, 'mixer_params': {'amplitude': 1e-4, 'decay': 2., 'disable_after': args.ramp},
-            'combine': True, 'trunc_params': {'chi_max': chis[0], 'svd_min': 1e-12}}
+            'combine': True, 'trunc_params': {'chi_max': chis[0], 'svd_min': args.svd_min}}
+    if args.svd_warm_start != 'default':
+        opts['svd_warm_start'] = False if args.svd_warm_start == 'off' else args.svd_warm_start
     eng = dmrg.TwoSiteDMRGEngine(psi, M, opts)
     t_ramp = []
     for c in chis:
@@ -1132,12 +1137,15 @@ def run_blocksparse(args):
             'data': 'product state -> DMRG (no synthetic tensors)', 'impl': 'b200',
             'config': {'workload': ('SpinChain XXZ L=%d chi=%d, U(1) Sz' if xxz else 'FermiHubbardChain L=%d chi=%d, U(1)xU(1) (N, Sz)')
                        % (L, chi) + ', two-site DMRG sweep after a chi ramp %r with the density-matrix mixer; timed sweeps: mixer '
-                       'off, adaptive Lanczos (reference defaults), svd_min=1e-12' % (chis,), 'L': L, 'chi': chi,
+                       'off, adaptive Lanczos (reference defaults), svd_min=%g, svd_warm_start=%s' % (chis, args.svd_min, args.svd_warm_start),
+                       'L': L, 'chi': chi,
                        'l2': 'working set (environments + MPS) >> 126 MB L2'},
             'clocks': clocks, 'gpu_launches': int(launches), 'ramp_sweep_s': t_ramp, 'chi_reached': int(max(psi.chi)),
             'result': {'E': float(eng.update_stats['E_total'][-1]), 'S_mid': float(psi.entanglement_entropy()[L // 2 - 1]),
                        'N_lanczos_mean': float(np.mean(eng.update_stats['N_lanczos'][-nb:])),
-                       'trunc_err_max': float(max(getattr(e, 'eps', e) for e in eng.update_stats['err'][-nb:]))},
+                       'trunc_err_max': float(max(getattr(e, 'eps', e) for e in eng.update_stats['err'][-nb:])),
+                       'svd_jacobi_sweeps_mean': float(np.mean(npc.svd_stats['jacobi_sweeps'][-nb:])),
+                       'svd_guess_used': npc.svd_stats.get('guess_used', 0)},
             'structure': {'theta_blocks': int(theta.stored_blocks), 'theta_shape': list(theta.shape),
                           'theta_largest_block': [int(x) for x in theta._layout.shapes[np.argmax(theta._layout.sizes)]],
                           'bond_sectors': int(psi.get_B(L // 2).get_leg('vL').block_number)},

@@ -1,7 +1,8 @@
 """Checkpoint exchange with the UNMODIFIED reference: a DMRG state computed by this package
 is converted with `tenpy_b200.tools.interop`, pickled, loaded by stock TeNPy (which measures the same energy and
-continues the run), and a reference state comes back.  Needs the reference checkout (/root/reference, build container
-only) -> skipped on the GPU box; device calls go to the numpy test double (this is host logic)."""
+continues the run), and a reference state comes back.  Needs the reference (the checkout of the build container or the
+offline install baseline/_ref that travels to the GPU box).  Twice: on the numpy test double (host logic) and, ``-m gpu``, with
+the state computed and re-imported on the B200."""
 import os
 import subprocess
 import sys
@@ -9,7 +10,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get('TENPY_REFERENCE', '/root/reference')
+sys.path.insert(0, ROOT)
+from tenpy_b200 import dropin  # noqa: E402
+
+REF = os.environ.get('TENPY_REFERENCE') or dropin.reference_path() or '/root/reference'
 
 SCRIPT = r'''
 import sys, pickle, warnings, io
@@ -18,8 +22,12 @@ sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/tests'); sys.path.
 warnings.simplefilter('ignore')
 import numpy as np
 from tenpy_b200 import backend
-from fake_device import FakeDeviceLib
-backend.use_library(FakeDeviceLib())
+if {fake!r}:
+    from fake_device import FakeDeviceLib
+    backend.use_library(FakeDeviceLib())
+else:
+    from tenpy_b200._lib import DeviceLib
+    backend.use_library(DeviceLib())
 from tenpy_b200.models import SpinChain as MySpinChain
 from tenpy_b200.networks.mps import MPS as MyMPS
 from tenpy_b200.algorithms import dmrg as mydmrg
@@ -62,11 +70,21 @@ print('E_device=%.12f E_continued=%.12f' % (res['E'], res2['E']))
 '''
 
 
-@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'tenpy')), reason='reference checkout not available')
-def test_checkpoint_roundtrip_with_reference(tmp_path):
+def _roundtrip(tmp_path, fake):
     script = tmp_path / 'interop.py'
-    script.write_text(SCRIPT.format(root=ROOT, ref=REF))
-    env = dict(os.environ, TENPY_NO_CYTHON='1', PYTHONDONTWRITEBYTECODE='1')
-    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+    script.write_text(SCRIPT.format(root=ROOT, ref=REF, fake=fake))
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1')
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env, cwd='/tmp')
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'E_device=' in out.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'tenpy')), reason='reference not available')
+def test_checkpoint_roundtrip_with_reference(tmp_path):
+    _roundtrip(tmp_path, True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'tenpy')), reason='reference not available (baseline/_ref)')
+def test_checkpoint_roundtrip_with_reference_gpu(tmp_path, gpu_lib):
+    _roundtrip(tmp_path, False)
