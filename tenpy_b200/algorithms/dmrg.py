@@ -19,7 +19,7 @@ from ..linalg import np_conserved as npc
 from ..linalg.krylov_based import LanczosGroundState
 from ..linalg.truncation import svd_theta
 from ..networks.mpo import MPOEnvironment
-from .mps_common import OneSiteH, TwoSiteH, DensityMatrixMixer, SubspaceExpansion
+from .mps_common import OneSiteH, TwoSiteH, DensityMatrixMixer, SubspaceExpansion, IdentityEnvRejected
 
 logger = logging.getLogger(__name__)
 
@@ -122,12 +122,13 @@ class TwoSiteDMRGEngine:
         self.sweeps = options.get('sweep_0', 0)
         self.time0 = time.time()
         self.mixer = None
-        # warm start of the Jacobi SVD from the previous update of the same bond (extension):
-        #   'subspace' (default): decompose theta inside the span of the previously kept isometry when the part
-        #                outside is below the truncation tolerance (truncation.svd_theta), no extra memory;
-        #   'full'     : rotate theta with the complete previous singular vector bases (2 (chi d)^2 doubles per bond);
-        #   False      : cold start every time.
-        ws = options.get('svd_warm_start', 'subspace')
+        # warm start of the Jacobi SVD from the previous update of the same bond (extension, off by default):
+        #   False      : cold start every time (default).  Measured on the B200, XXZ L=100 chi=1024 (profiles/r02j): cold
+        #                3.78 s per sweep, 'full' 3.56 s, 'subspace' 4.02 s; TFI chi=1024: cold is fastest;
+        #   'full'     : rotate theta with the complete previous singular vector bases (keeps 2 (chi d)^2 doubles per bond);
+        #   'subspace' : decompose theta inside the span of the previously kept isometry when the part outside is below
+        #                the truncation tolerance (truncation.svd_theta); keeps the truncated (U, VH) of every bond.
+        ws = options.get('svd_warm_start', False)
         self.svd_warm_start = 'full' if ws is True else ws
         self._svd_guess = {}
         self.env = MPOEnvironment(psi, model.H_MPO, psi)
@@ -368,6 +369,8 @@ class TwoSiteDMRGEngine:
             self.eff_H.mpo_apply = self.options['mpo_apply']
         if 'identity_env' in self.options:
             self.eff_H.identity_env = bool(self.options['identity_env'])
+        # this engine's Lanczos calls `eff_H.deferred_check()` after its first read-back (and `diag` restarts on rejection)
+        self.eff_H.identity_check = self.options.get('identity_check', 'deferred')
         theta = self.psi.get_theta(self.i0, n=self.n_optimize)
         return self.eff_H.combine_theta(theta)
 
@@ -394,7 +397,10 @@ class TwoSiteDMRGEngine:
                                               self.eff_H.N < self.options.get('max_N_for_ED', 400)):
             E, theta = full_diag_effH(self.eff_H, theta_guess, keep_sector=True)
         else:
-            E, theta, N = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params).run()
+            try:
+                E, theta, N = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params).run()
+            except IdentityEnvRejected:      # the deferred test of the matvec shortcut failed: plain contraction order
+                E, theta, N = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params).run()
         ov_change = 1. - abs(npc.inner(theta_guess, theta, 'labels', do_conj=True))
         return E, theta, N, ov_change
 

@@ -165,6 +165,11 @@ def _get_RHeff(env, i, eff_H):
     return env._contract_RHeff(i)
 
 
+class IdentityEnvRejected(Exception):
+    """raised by `TwoSiteH.deferred_check` when the environments turn out not to have identity components: the caller
+    restarts its iteration, the effective Hamiltonian has switched the shortcut off"""
+
+
 class TwoSiteH:
     r"""Effective Hamiltonian ``LP--W0--W1--RP`` acting on the two-site wave function (reference :1245).
 
@@ -191,6 +196,11 @@ class TwoSiteH:
     # skip the identity components of the environments in the split-order matvec (see _identity_env_setup): host logic on
     # the GPU-verified kernels, results checked against the reference goldens; engine option `identity_env` switches it off
     identity_env = True
+    # 'immediate' (default): the numerical test LP[IdL] = RP[IdR] = 1 costs two blocking reads before the first matvec of
+    # the bond; 'deferred': it is evaluated on the device and read back by the caller at its next synchronisation
+    # (`deferred_check`; on failure `IdentityEnvRejected` is raised and the caller restarts without the shortcut) -- only
+    # for callers that do call `deferred_check` (the DMRG engines set it; their Lanczos checks after its first read-back)
+    identity_check = 'immediate'
     stats = {'identity_env_bonds': 0, 'identity_env_rejected': 0}     # diagnostics (how often the shortcut applied)
 
     def __init__(self, env, i0, combine=False, move_right=True, matvec_order='auto'):
@@ -230,6 +240,8 @@ class TwoSiteH:
         if self._W01 is None:
             self._W01 = npc.tensordot(self.W0, self.W1, axes=['wR', 'wL'])   # wL p0 p0* p1 p1* wR  (D^2 d^4 numbers)
         rec = getattr(self, '_dense_recipe', None)
+        if rec is None and not self._dense_recipe_off and self.identity_env and self.mpo_apply == 'fused':
+            rec = self._dense_recipe_from_cache(theta)
         if rec is not None and theta._layout is rec['lay'] and theta._labels == rec['labels']:
             return self._dense_recipe_run(theta, rec)
         th = theta.split_legs(['(vL.p0)', '(p1.vR)'], _view=True)            # vL p0 p1 vR (read only here)
@@ -266,6 +278,23 @@ class TwoSiteH:
         self._id_env = ok
         return ok
 
+    def deferred_check(self):
+        """Called by the eigensolver right after one of its own device synchronisations: evaluates the pending test of the
+        identity-environment shortcut (free now); raises `IdentityEnvRejected` if it failed."""
+        pending = getattr(self, '_id_check', None)
+        if not pending:
+            return
+        self._id_check = None
+        from .. import backend
+        for out, lim in pending:
+            if not backend.read_scalar(out) <= lim:
+                self._id_env = False
+                self._dense_recipe = None
+                self._dense_recipe_off = True
+                TwoSiteH.stats['identity_env_bonds'] -= 1
+                TwoSiteH.stats['identity_env_rejected'] += 1
+                raise IdentityEnvRejected('environment component differs from the identity')
+
     def _identity_env_prepare(self):
         H = getattr(self, '_H_mpo', None)
         if H is None:
@@ -277,14 +306,27 @@ class TwoSiteH:
         D_l, D_r = LP.get_leg('wR').ind_len, RP.get_leg('wL').ind_len
         if D_l < 2 or D_r < 2:
             return False
+        self._id_check = None
+        pending = []
         for part, idx, lab in ((LP, IdL, 'wR'), (RP, IdR, 'wL')):
             comp = part.take_slice(idx, lab)
             if np.any(comp.qtotal != 0):
                 return False
             eye = _cached_eye(comp)
-            dev = npc.norm(comp - eye) if comp.legs[1].qconj == eye.legs[1].qconj else np.inf
-            if not dev <= 1.e-11 * np.sqrt(comp.shape[0]):
+            if comp.legs[1].qconj != eye.legs[1].qconj:
                 return False
+            diff = comp - eye
+            if self.identity_check == 'deferred' and diff._layout.nblocks:
+                # |LP[IdL] - 1|^2 stays on the device; it is read together with the Lanczos scalars (the next unavoidable
+                # synchronisation, `deferred_check`), so the set-up costs no round trip of its own
+                from .. import backend
+                out = backend.empty(1)
+                backend.get_lib().dot(diff._layout.size, diff._buf, diff._buf, backend.dot_scratch(), out)
+                pending.append((out, (1.e-11 * np.sqrt(comp.shape[0]))**2))
+            elif not npc.norm(diff) <= 1.e-11 * np.sqrt(comp.shape[0]):
+                return False
+        if pending:
+            self._id_check = pending
         only_l, only_r = np.zeros(D_l, bool), np.zeros(D_r, bool)
         only_l[IdL], only_r[IdR] = True, True
 
@@ -293,12 +335,15 @@ class TwoSiteH:
             rest.iproject(~only, label)
             one.iproject(only, label)
             return rest, one
-        self._LP_rest, LP_one = pieces(LP, 'wR', only_l)
-        self._RP_rest, RP_one = pieces(RP, 'wL', only_r)
+
+        def rest_of(arr, label, only):           # all other components (one block move) and the unit leg of the identity one
+            rest = arr.copy(deep=True)
+            rest.iproject(~only, label)
+            return rest, arr.get_leg(label).project(only)[2]
         # private copies, constant for the lifetime of this object: their int8 digit planes (npc.OZAKI) are made once
+        self._LP_rest, self._leg_IdL = rest_of(LP, 'wR', only_l)
+        self._RP_rest, self._leg_IdR = rest_of(RP, 'wL', only_r)
         self._LP_rest._oz_const = self._RP_rest._oz_const = True
-        self._leg_IdL = LP_one.get_leg('wR')     # unit legs carrying the charge of the identity component
-        self._leg_IdR = RP_one.get_leg('wL')
         # everything below depends on the MPO and the bond only (not on the state): made once per bond, kept on the MPO
         cache = H.__dict__.setdefault('_b200_two_site_cache', {})
         ent = cache.get(self.i0)
@@ -388,6 +433,12 @@ class TwoSiteH:
         if plan1 is None or plan2 is None:
             self._dense_recipe_off = True
             return
+        ent = getattr(self, '_mpo_cache', None)
+        if ent is not None:
+            ent['recipe_geom'] = {'theta_lay': out._layout, 'labels': list(out._labels), 'plan1': plan1[2], 'plan2': plan2[2],
+                                  'shape_t1': tuple(t1.shape), 'n_t1': int(t1._layout.size), 'n_yr': int(y_rest._layout.size),
+                                  'n_yi': int(y_id._layout.size),
+                                  'padded': any(a._layout.has_padding for a in (t1, y_rest, y_id, out))}
         self._dense_recipe = {
             'lay': out._layout, 'labels': list(out._labels), 'template': out,
             'g1': (chi_l * Dm1, d0 * d1 * chi_r, chi_l), 'plan1': plan1[2],          # (m, n, k) of LP_rest . theta
@@ -399,6 +450,37 @@ class TwoSiteH:
         }
 
     _dense_recipe_off = False
+
+    def _dense_recipe_from_cache(self, theta):
+        """From the second visit of a bond on (same MPO, same shapes) the kernel sequence is known before the first matvec:
+        set up the identity components and bind the recorded geometry to this bond's buffers -- the Array-level route is
+        not taken at all.  None if the bond has no recorded geometry (first visit) or anything differs."""
+        H = getattr(self, '_H_mpo', None)
+        ent = None if H is None else H.__dict__.get('_b200_two_site_cache', {}).get(self.i0)
+        geom = None if ent is None else ent.get('recipe_geom')
+        if geom is None or 'M_id' not in ent or theta._layout is not geom['theta_lay'] or theta._labels != geom['labels']:
+            return None
+        if getattr(self, '_id_env', None) is False or not self._identity_env_setup():
+            return None
+        chi_l, Dm1, d0, d1, chi_r = geom['shape_t1']
+        if self._LP_rest.shape != (chi_l, Dm1, chi_l) or self._RP_rest.get_leg('wL').ind_len != Dm1 or \
+                self._LP_rest._layout.nblocks != 1 or self._RP_rest._layout.nblocks != 1:
+            return None
+        from .. import backend
+        self._M_id, self._N1, self._fused_legs = ent['M_id'], ent['N1'], ent['fused_legs']
+        self._RP_rest_t = self._RP_rest.transpose(['wL', 'vL', 'vL*'])
+        self._RP_rest_t._oz_const = True
+        if self._RP_rest_t.shape != (Dm1, chi_r, chi_r):
+            return None
+        self._dense_recipe = {
+            'lay': geom['theta_lay'], 'labels': geom['labels'], 'template': theta.copy(deep=False),
+            'g1': (chi_l * Dm1, d0 * d1 * chi_r, chi_l), 'plan1': geom['plan1'],
+            'g2': (chi_l * d0 * d1, chi_r, Dm1 * chi_r), 'plan2': geom['plan2'],
+            'mid': (Dm1 * d0 * d1, d0 * d1, self._N1, d0 * d1, chi_l, chi_r),
+            'n_t1': geom['n_t1'], 'n_yr': geom['n_yr'], 'n_yi': geom['n_yi'],
+            'alloc': backend.zeros if geom['padded'] else backend.empty,
+        }
+        return self._dense_recipe
 
     def _dense_recipe_run(self, theta, rec):
         from .. import backend

@@ -134,6 +134,9 @@ class LanczosGroundState(KrylovBased):
                                        sc[2 * k + 1:2 * k + 2])
                 k += 1
             vals = backend.to_host(sc[:2 * k])                        # the one synchronisation of this chunk
+            check = getattr(self.H, 'deferred_check', None)
+            if check is not None:
+                check()                                               # tests the operator postponed to this point
             for kk in range(done_k, k):
                 h[kk, kk] = vals[2 * kk]
                 self._calc_result_krylov(kk)
@@ -166,6 +169,8 @@ class LanczosGroundState(KrylovBased):
             self._to_cache(w)
             w = self.H.matvec(w)
             alpha = float(npc.inner(w, self._cache[-1], axes='range', do_conj=True))
+            if k == 0 and getattr(self.H, 'deferred_check', None) is not None:
+                self.H.deferred_check()                                # tests the operator postponed to its first read-back
             h[k, k] = alpha
             self._calc_result_krylov(k)
             fused = (not self.reortho) and w._layout.same_blocks(self._cache[-1]._layout) and \

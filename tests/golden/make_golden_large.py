@@ -55,6 +55,7 @@ def run_reference(name):
             # Schmidt values that are determined by the physics at the convergence level of the run (weight > 1e-12); the
             # count of the smaller ones depends on rounding noise (the energy does not fix components of weight 1e-24)
             'n_schmidt_above_1e-6': [int(np.sum(np.asarray(psi.get_SL(i)) > 1.e-6)) for i in range(1, L)],
+            'schmidt_above_1e-7': [[float(x) for x in np.sort(np.asarray(psi.get_SL(i)))[::-1] if x > 1.e-7] for i in range(1, L)],
             'schmidt_centre': [float(x) for x in np.sort(sv)[::-1]], 'sweeps': int(eng.sweeps), 'seconds': dt,
             'sweep_times': [float(x) for x in np.diff([0.] + list(eng.sweep_stats['time']))],
             'host_cpus': os.cpu_count(), 'L': L, 'chi_max': case['chi']}

@@ -508,3 +508,26 @@ def test_matvec_identity_env(fake_device):
             'matvec_order': 'split', 'identity_env': True}
     res, psi = _run_dmrg(M, ['up', 'down'] * (L // 2), opts)
     assert abs(res['E'] - g['xxz_E']) < 1e-10 * abs(g['xxz_E'])
+
+
+def test_identity_env_deferred_check_rejects(fake_device):
+    """The engine defers the numerical test of the identity-environment shortcut to the first read-back of its Lanczos
+    iteration; on a state that is NOT in canonical form the test fails, the iteration restarts with the plain contraction
+    order and the run gives the same result as with the shortcut switched off."""
+    from tenpy_b200.models import TFIChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    from tenpy_b200.algorithms.mps_common import TwoSiteH
+    L = 10
+    M = TFIChain({'L': L, 'J': 1., 'g': 1.3, 'conserve': None})
+    res = {}
+    for ident in (True, False):
+        psi = MPS.from_product_state(M.lat_sites, ['up'] * L)
+        psi._B[6] = psi._B[6] * 1.7          # breaks the right-canonical form: RP[IdR] = 1.7^2 left of site 6
+        rej0 = TwoSiteH.stats['identity_env_rejected']
+        out = dmrg.run(psi, M, {'mixer': None, 'max_E_err': 1e-11, 'combine': True, 'matvec_order': 'split',
+                                'diag_method': 'lanczos', 'identity_env': ident,
+                                'trunc_params': {'chi_max': 20, 'svd_min': 1e-10}})
+        res[ident] = (out['E'], TwoSiteH.stats['identity_env_rejected'] - rej0)
+    assert res[True][1] >= 1                      # the deferred test fired at least once ...
+    assert abs(res[True][0] - res[False][0]) < 1e-10 * abs(res[False][0])      # ... and the result is unaffected

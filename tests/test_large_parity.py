@@ -61,8 +61,12 @@ def test_large_dmrg_matches_reference(gpu_lib, name):
     for i, (c, gc) in enumerate(zip(chi, gchi)):
         if gc == cap or gc == min(2 ** (i + 1), 2 ** (L - 1 - i)) or gc == min(4 ** (i + 1), 4 ** (L - 1 - i)):
             assert c == gc, (i, c, gc)
-    n_phys = [int(np.sum(np.asarray(psi.get_SL(i)) > 1.e-6)) for i in range(1, L)]
-    assert n_phys == g['n_schmidt_above_1e-6']
+    for i in range(1, L):
+        mine = np.sort(np.asarray(psi.get_SL(i)))[::-1]
+        ref_i = np.array(g['schmidt_above_1e-7'][i - 1])
+        n = min(len(mine), len(ref_i))
+        assert np.max(np.abs(mine[:n] - ref_i[:n])) <= 1e-8, (i, float(np.max(np.abs(mine[:n] - ref_i[:n]))))
+        assert np.all(mine[n:] < 1.e-7 + 1.e-8) and np.all(ref_i[n:] < 1.e-7 + 1.e-8), i      # unmatched values: below the cut
     sv = np.sort(np.asarray(psi.get_SL(L // 2)))[::-1]
     ref = np.array(g['schmidt_centre'])
     k = min(len(sv), len(ref))
