@@ -116,24 +116,19 @@ def fast_two_site_engine():
             self._RHeff = getattr(self, 'RHeff', None)
 
         matvec_order = 'auto'
-        SPLIT_MIN_BLOCK = _EngineH.SPLIT_MIN_BLOCK
-        mpo_apply = _EngineH.mpo_apply
-        identity_env = _EngineH.identity_env
-        stats = _EngineH.stats
-        _use_split = _EngineH._use_split
-        _matvec_split = _EngineH._matvec_split
-        _identity_env_setup = _EngineH._identity_env_setup
-        _identity_env_prepare = _EngineH._identity_env_prepare
-        _matvec_split_identity = _EngineH._matvec_split_identity
-        _matvec_split_identity_tail = _EngineH._matvec_split_identity_tail
-        _split_t2_views = staticmethod(_EngineH._split_t2_views)
-        _apply_W01_fused_identity = _EngineH._apply_W01_fused_identity
-        _apply_W01_fused = _EngineH._apply_W01_fused
 
         def matvec(self, theta):
             if self.combine and self._use_split(theta):
                 return self._matvec_split(theta, theta.get_leg_labels())
             return super().matvec(theta)
+
+    # the device-optimised contraction routes of the engine's own TwoSiteH (everything but the constructor and the
+    # environment updates, which stay the reference's): methods and their class-level switches, by name prefix
+    take = ('_matvec_split', '_identity_env', '_dense_recipe', '_apply_W01', '_split_t2_views', '_use_split', 'deferred_check',
+            'identity_check', 'identity_env', 'mpo_apply', 'SPLIT_MIN_BLOCK', 'stats')
+    for name, val in vars(_EngineH).items():
+        if name.startswith(take) and name not in vars(B200TwoSiteH):
+            setattr(B200TwoSiteH, name, val)
 
     class B200TwoSiteDMRGEngine(ref_dmrg.TwoSiteDMRGEngine):
         EffectiveH = B200TwoSiteH
