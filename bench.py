@@ -682,7 +682,7 @@ def run_b200(args):
     dominant = max(shares, key=shares.get) if shares else 'gemm'
     roofline = roof['svd'] if dominant == 'svd' else roof['gemm']
     roofline = dict(roofline)
-    roofline['kernel'] = 'jacobi_gram/eig/apply_kernel (block SVD)' if dominant == 'svd' else 'grouped_gemm_kernel<64,64,2,2,1> (matvec)'
+    roofline['kernel'] = 'jacobi_gram/eig/apply_kernel (block SVD)' if dominant == 'svd' else 'oz_gemm_kernel (matvec, tcgen05 kind::i8)'
     roofline['share_of_step'] = shares.get(dominant)
     if e2e:
         e2e['value'] = float(allst[:, 3].max()) / world
@@ -942,36 +942,71 @@ def kernel_probes(lib, chi, d, D):
     vL, vR, lp = (npc.LegCharge.from_trivial(chi, ci, +1), npc.LegCharge.from_trivial(chi, ci, -1),
                   npc.LegCharge.from_trivial(d, ci, +1))
     theta = rnd([lL, lR])
-    # the two large GEMMs of the matvec as the sweep runs it ('split' order): LP . theta and (..) . RP
-    LP, th4 = rnd([vR.conj(), lW, vR]), rnd([vL, lp, lp, vR])                 # (chi D x chi) . (chi x d^2 chi)
-    t3, RP = rnd([vL, lp, lp, vR, lW]), rnd([vR.conj(), lW.conj(), vR])        # (chi d^2 x chi D) . (chi D x chi)
-    reps = 5
-    for _ in range(3):
-        npc.tensordot(LP, th4, axes=[2, 0])
-        npc.tensordot(t3, RP, axes=[[3, 4], [0, 1]])
+    # the two large products of the matvec as the sweep runs them (identity-environment route): the D - 1 non-identity
+    # components of LP onto theta and the W0 W1 . theta intermediate onto those of RP, on the int8 tensor path with 7 digit
+    # planes (csrc/ozaki.cu); the digit planes of LP / RP are cached per bond, those of theta / the intermediate are
+    # produced by the split kernels once per matvec (timed separately: `split_ms_per_operand`)
+    from tenpy_b200.linalg.np_conserved import OZAKI
+    s7 = int(OZAKI['slices_matvec'])
+    Dr = max(D - 1, 1)
+    shapes = [(chi * Dr, d * d * chi, chi), (chi * d * d, chi, chi * Dr)]      # (m, n, k)
+    ops, ms_mm, ms_split = [], [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(reps):
-        npc.tensordot(LP, th4, axes=[2, 0])
-        npc.tensordot(t3, RP, axes=[[3, 4], [0, 1]])
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / reps / 2.          # per launch
-    flops = 2. * D * d**2 * chi**3                    # per launch
+    reps = 10
+    for (m_, n_, k_) in shapes:
+        A = torch.randn(m_ * k_, dtype=torch.float64, device=dev)
+        B = torch.randn(k_ * n_, dtype=torch.float64, device=dev)
+        C = torch.empty(m_ * n_, dtype=torch.float64, device=dev)
+        a_s = lib.ozaki_split(m_, k_, A, k_, 1, s7)
+        b_s = lib.ozaki_split(n_, k_, B, 1, n_, s7)
+        for _ in range(3):
+            lib.ozaki_mm(m_, n_, k_, s7, a_s, b_s, C, n_)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            lib.ozaki_mm(m_, n_, k_, s7, a_s, b_s, C, n_)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_mm.append(ev0.elapsed_time(ev1) / reps)
+        ev0.record()
+        for _ in range(reps):
+            lib.ozaki_split(n_, k_, B, 1, n_, s7)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_split.append(ev0.elapsed_time(ev1) / reps)
+        ops.append((A, B, C))
+    lib.ozaki_check_abort()
+    # parity of the timed kernel at the timed size (size-independent property: linearity in a random probe vector,
+    # (A B) x = A (B x) evaluated in FP64 on the device)
+    m_, n_, k_ = shapes[-1]
+    A, B, C = ops[-1]
+    x = torch.randn(n_, dtype=torch.float64, device=dev)
+    lhs = C.view(m_, n_) @ x
+    rhs = A.view(m_, k_) @ (B.view(k_, n_) @ x)
+    scale = A.view(m_, k_).abs() @ (B.view(k_, n_).abs() @ x.abs())
+    oz_err = float(((lhs - rhs).abs() / scale).max())
+    del ops
+    ms = float(np.mean(ms_mm))
+    flops = 2. * Dr * d**2 * chi**3                  # per launch (FP64-equivalent)
+    n_prod = s7 * (s7 + 1) // 2                      # exact int8 slice products per FP64 product
     tf = flops / (ms * 1e-3) / 1e12
     traffic, pipe_pct, ncu_src = gemm_ncu_numbers() if (chi, d, D) == (1024, 2, 3) else (None, None, None)
-    sm_mhz = peaks.get('sm_max_mhz', 1965.0)
-    gemm = {'bound': 'tensor', 'achieved': tf, 'peak': FP64_TENSOR_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-            'frac': tf / FP64_TENSOR_PEAK_TFLOPS, 'traffic': traffic, 'ms_per_launch': ms,
-            'algorithmic_bytes_per_launch': 8. * (D * chi * chi + chi * d * d * chi + D * chi * d * d * chi),
-            'tensor_pipe_active_pct_ncu': pipe_pct, 'ncu_source': ncu_src,
-            'peak_note': 'FP64 tensor (DMMA) pipe: 128 flop/clk/SM x 148 SMs x %.0f MHz = %.1f TFLOP/s (nominal B200 '
-                         'spec 37; MEASURED_PEAKS.json has only bf16: %.0f TFLOP/s %s); the ncu capture shows the pipe '
-                         '%s %% active at this rate' % (sm_mhz, 128 * 148 * sm_mhz * 1e6 / 1e12,
-                                                        peaks.get('bf16_tflops', 0.), kind, pipe_pct),
-            'algorithmic': '2 D d^2 chi^3 = %.3e flop per launch: (chi D x chi).(chi x d^2 chi) and '
-                           '(chi d^2 x chi D).(chi D x chi), the two large GEMMs of one matvec' % flops}
+    int8_peak = 2. * peaks.get('bf16_tflops', 0.)    # tcgen05 kind::i8 runs at twice the bf16 rate
+    peak_equiv = int8_peak / n_prod
+    gemm = {'bound': 'tensor', 'achieved': tf, 'peak': peak_equiv, 'unit': 'TFLOP/s', 'frac': tf / peak_equiv if peak_equiv else None,
+            'traffic': traffic, 'ms_per_launch': ms, 'ms_per_launch_by_shape': {'%dx%dx%d' % sh: t for sh, t in zip(shapes, ms_mm)},
+            'int8_tops_achieved': tf * n_prod, 'int8_tops_peak': int8_peak, 'frac_of_nominal_int8_4500': tf * n_prod / 4500., 'digit_planes': s7, 'int8_products_per_fp64_product': n_prod,
+            'split_ms_per_operand': float(np.mean(ms_split)),
+            'fp64_dmma_peak_tflops': FP64_TENSOR_PEAK_TFLOPS, 'frac_of_fp64_dmma_peak': tf / FP64_TENSOR_PEAK_TFLOPS,
+            'algorithmic_bytes_per_launch': float(s7 * (shapes[0][0] * shapes[0][2] + shapes[0][1] * shapes[0][2]) + 8 * shapes[0][0] * shapes[0][1]),
+            'tensor_pipe_active_pct_ncu': pipe_pct, 'ncu_source': ncu_src, 'rel_err_vs_fp64_probe': oz_err,
+            'peak_note': 'achieved = FP64-equivalent flops (2 m n k) per launch / CUDA-event time of oz_gemm_kernel alone, operands pre-split '
+                         'as in the sweep; peak = int8 tensor peak / %d slice products, int8 peak = 2 x bf16_tflops of MEASURED_PEAKS.json '
+                         '(%.0f TFLOP/s %s, burst) = %.0f Top/s (nominal 4500; MMA-only ceiling of this tile shape measured by '
+                         'profiles/tc_i8_probe.cu: 4000-4540); the FP64 tensor (DMMA) pipe the round-1 kernel ran on peaks at %.0f TFLOP/s'
+                         % (n_prod, peaks.get('bf16_tflops', 0.), kind, int8_peak, FP64_TENSOR_PEAK_TFLOPS),
+            'algorithmic': '2 (D-1) d^2 chi^3 = %.3e FP64-equivalent flop per launch = %.3e int8 op: (chi (D-1) x chi).(chi x d^2 chi) and '
+                           '(chi d^2 x chi (D-1)).(chi (D-1) x chi), the two large products of one matvec' % (flops, flops * n_prod)}
     # SVD of the centre theta: bytes = 8 (mn + mk + k + kn)
     from tenpy_b200.linalg.np_conserved import svd
     svd(theta)

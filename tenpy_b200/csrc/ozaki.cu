@@ -152,6 +152,7 @@ struct OzGemmArgs {
     int32_t cps;                 // k chunks per pipeline stage (4 or 2)
     int32_t nstages;
     int32_t accumulate;          // 0: C = A.B, 1: C += A.B
+    int32_t acc_group;           // accumulators (diagonals) per pass: 4 or 2
     int32_t *abort_flag;
     long long *dbg;              // optional (B200_OZ_DEBUG): cycle counters of CTA 0, see b200_ozaki_mm_f64
 };
@@ -166,14 +167,17 @@ __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
-    __shared__ uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full, acc_empty;
+    __shared__ uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     using namespace tc05;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = p.slices, cps = p.cps, nst = p.nstages;
     const uint32_t tile_bytes = (uint32_t)cps * OZ_CHUNK_BYTES;       // one slice tile of a stage
     const uint32_t stage_bytes = 2u * s * tile_bytes;
-    const int npass = (s + 3) / 4;
+    // accumulators per pass: 4 (all of TMEM, the epilogue and the next pass alternate) or 2 (two halves of TMEM, the epilogue
+    // of one half overlaps the MMAs of the other; more passes, i.e. more operand traffic)
+    const int G = p.acc_group;
+    const int npass = (s + G - 1) / G;
     const int ksteps = p.kc / cps;                                    // pipeline stages per pass
     const int mt_count = (p.M + OZ_TILE - 1) / OZ_TILE, nt_count = (p.N + OZ_TILE - 1) / OZ_TILE;
     const int ntiles = mt_count * nt_count;
@@ -183,8 +187,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(&acc_full, 1);
-        mbar_init(&acc_empty, 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(&tmem_slot, 512);
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             const int mt = tile % mt_count, nt = tile / mt_count;
             for (int g = npass - 1; g >= 0 && ok; --g) {
-                const int nsl = s - 4 * (npass - 1 - g);             // slices 0 .. nsl-1 of both operands are needed (= d_hi + 1)
+                const int nsl = s - G * (npass - 1 - g);             // slices 0 .. nsl-1 of both operands are needed (= d_hi + 1)
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int slot = it % nst;
                     const long long tw = clock64();
@@ -231,9 +237,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         long long t_full = 0, t_acc = 0, t0 = clock64();
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
-                const int d_hi = s - 1 - 4 * (npass - 1 - g), d_lo = max(0, d_hi - 3);
+                const int d_hi = s - 1 - G * (npass - 1 - g), d_lo = max(0, d_hi - G + 1);
+                const int half = (G == 2) ? (int)(pass_it & 1u) : 0;           // which set of accumulators
+                const uint32_t use = (G == 2) ? (pass_it >> 1) : pass_it;       // how often this set has been used before
+                const uint32_t tbase = tmem + (uint32_t)half * 2u * OZ_TILE;
                 long long tw = clock64();
-                ok = mbar_wait(&acc_empty, (pass_it & 1) ^ 1, p.abort_flag);   // epilogue has drained the accumulators
+                ok = mbar_wait(&acc_empty[half], (use & 1) ^ 1, p.abort_flag);   // epilogue has drained these accumulators
                 t_acc += clock64() - tw;
                 if (!ok) break;
                 fence_after_sync();
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                     const uint64_t da0 = oz_desc(sa), db0 = oz_desc(sa + (uint32_t)s * tile_bytes);
                     const uint32_t tile16 = tile_bytes >> 4, kstep16 = (2u * OZ_CHUNK_BYTES) >> 4;
                     for (int d = d_lo; d <= d_hi; ++d) {
-                        const uint32_t acc = tmem + (uint32_t)(d - d_lo) * OZ_TILE;
+                        const uint32_t acc = tbase + (uint32_t)(d - d_lo) * OZ_TILE;
                         for (int t = 0; t <= d; ++t) {                 // all pairs (t, u = d - t) of the diagonal
                             const uint64_t ad = da0 + (uint64_t)((uint32_t)t * tile16);
                             const uint64_t bd = db0 + (uint64_t)((uint32_t)(d - t) * tile16);
@@ -260,7 +269,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                     }
                     mma_commit(&empty_bar[slot]);                      // slot free once these MMAs have read it
                 }
-                if (ok) mma_commit(&acc_full);                         // accumulators of this pass complete
+                if (ok) mma_commit(&acc_full[half]);                   // accumulators of this pass complete
             }
         }
         if (p.dbg && blockIdx.x == 0) {
@@ -278,9 +287,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
             const int mt = tile % mt_count, nt = tile / mt_count;
             const double *sbp = p.sB + (int64_t)nt * OZ_TILE;
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
-                const int d_hi = s - 1 - 4 * (npass - 1 - g), d_lo = max(0, d_hi - 3);
+                const int d_hi = s - 1 - G * (npass - 1 - g), d_lo = max(0, d_hi - G + 1);
+                const int half = (G == 2) ? (int)(pass_it & 1u) : 0;           // which set of accumulators
+                const uint32_t use = (G == 2) ? (pass_it >> 1) : pass_it;       // how often this set has been used before
+                const uint32_t tbase = tmem + (uint32_t)half * 2u * OZ_TILE;
                 const long long tw = clock64();
-                ok = mbar_wait(&acc_full, pass_it & 1, p.abort_flag);
+                ok = mbar_wait(&acc_full[half], use & 1, p.abort_flag);
                 t_wait += clock64() - tw;
                 if (!ok) break;
                 fence_after_sync();
@@ -292,13 +304,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                 for (int c0 = 0; c0 < OZ_TILE; c0 += 32) {
                     double h[32];
                     uint32_t r[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d_hi - d_lo) * OZ_TILE + c0, r);
+                    tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(d_hi - d_lo) * OZ_TILE + c0, r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         h[j] = __hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0;
                     for (int d = d_hi - 1; d >= d_lo; --d) {
-                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d - d_lo) * OZ_TILE + c0, r);
+                        tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(d - d_lo) * OZ_TILE + c0, r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -344,7 +356,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                     }
                 }
                 fence_before_sync();
-                mbar_arrive(&acc_empty);
+                mbar_arrive(&acc_empty[half]);
             }
         }
         if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
@@ -451,6 +463,8 @@ extern "C" int b200_ozaki_mm_f64(int64_t m, int64_t n, int64_t k, int32_t slices
     }
     // pipeline shape: as many k chunks per stage as leave at least two stages in shared memory
     static const int force_cps = getenv("B200_OZ_CPS") ? atoi(getenv("B200_OZ_CPS")) : 0;   // tuning knob (2 or 4)
+    static const int force_acc = getenv("B200_OZ_ACC") ? atoi(getenv("B200_OZ_ACC")) : 0;   // tuning knob (2 or 4)
+    p.acc_group = force_acc == 2 ? 2 : 4;
     p.cps = force_cps == 2 ? 2 : 4;
     int64_t stage = 2LL * slices * p.cps * OZ_CHUNK_BYTES;
     if (OZ_SMEM_BUDGET / stage < 2) {
