@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument('--svd-warm-start', default='default', choices=['default', 'off', 'subspace', 'full'],
                     help='--workload xxz|hubbard: engine option svd_warm_start (default: the engine default)')
     ap.add_argument('--svd-min', type=float, default=1e-10, help='--workload xxz|hubbard: truncation threshold svd_min')
+    ap.add_argument('--svd-inner-sweeps', type=int, default=0,
+                    help='--workload xxz|hubbard: inner sweeps of the pivot eigen-solver of the block SVD (0: library default)')
     ap.add_argument('--ramp', type=int, default=6, help='--workload xxz|hubbard: sweeps of the chi ramp (doubling from 32)')
     ap.add_argument('--driver', default='own', choices=['own', 'reference'],
                     help="'reference': the unmodified tenpy TwoSiteDMRGEngine (tenpy_b200.dropin) drives the sweep on the device "
@@ -1107,6 +1109,8 @@ def run_blocksparse(args):
     from tenpy_b200.linalg import np_conserved as npc
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     lib = backend.use_library(DeviceLib())
+    if args.svd_inner_sweeps:
+        lib.svd_set_eig_inner_sweeps(args.svd_inner_sweeps)
     xxz = args.workload == 'xxz'
     L = args.L if args.L != 100 or xxz else 64
     chi = args.chi if args.chi != 1024 or xxz else 2048
@@ -1173,7 +1177,7 @@ def run_blocksparse(args):
             'config': {'workload': ('SpinChain XXZ L=%d chi=%d, U(1) Sz' if xxz else 'FermiHubbardChain L=%d chi=%d, U(1)xU(1) (N, Sz)')
                        % (L, chi) + ', two-site DMRG sweep after a chi ramp %r with the density-matrix mixer; timed sweeps: mixer '
                        'off, adaptive Lanczos (reference defaults), svd_min=%g, svd_warm_start=%s' % (chis, args.svd_min, args.svd_warm_start),
-                       'L': L, 'chi': chi,
+                       'L': L, 'chi': chi, 'svd_inner_sweeps': args.svd_inner_sweeps or 'library default',
                        'l2': 'working set (environments + MPS) >> 126 MB L2'},
             'clocks': clocks, 'gpu_launches': int(launches), 'ramp_sweep_s': t_ramp, 'chi_reached': int(max(psi.chi)),
             'result': {'E': float(eng.update_stats['E_total'][-1]), 'S_mid': float(psi.entanglement_entropy()[L // 2 - 1]),

@@ -19,8 +19,8 @@
 // by ONE bulk async copy of the TMA unit (cp.async.bulk, SASS UBLKCP) and is directly the un-swizzled K-major core-matrix
 // layout tcgen05 expects: core matrix (8 rows x 16 B) contiguous, LBO (K direction) = 2048 B, SBO (row direction) = 128 B.
 //
-// Kernel (persistent, one CTA per SM, 8 warps): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
-// allocation, warps 4..7 = epilogue (TMEM -> registers -> FP64 -> C).  512 TMEM columns = 4 int32 accumulators of
+// Kernel (persistent, one CTA per SM, 12 warps): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocation, warps 4..11 = epilogue (TMEM -> registers -> FP64 -> C; two warps per TMEM lane quarter, 64 columns each).  512 TMEM columns = 4 int32 accumulators of
 // 128 x 128, so the diagonals are processed in passes of up to 4, least significant pass first and the groups aligned at the
 // top (s = 7: d = 3..6 then d = 0..2): the last pass needs the fewest slices; within a pass every loaded slice tile is
 // reused by up to 4 MMAs.
@@ -139,6 +139,145 @@ __global__ void oz_split_kernel(const double *__restrict__ X, int64_t rows, int6
     }
 }
 
+// ---- single-launch split (slices <= OZ_FUSED_MAX_SLICES): row maximum and digits in one kernel ---------------------------
+// One CTA = 32 rows x all k.  Phase 1 streams the rows once for the maximum; phase 2 re-reads them (from L2: the CTA has
+// just touched these 32 k doubles) in blocks of 128 k through shared memory, so that both the global reads and the 16-byte
+// digit stores are coalesced for either operand orientation.  The digits come from ONE conversion per element:
+//   X = rint(x 2^-e 2^(6 + 7 (s-1)))  (int64, |X| <= 2^(6 + 7 (s-1)) <= 2^62),   X = sum_t d_t 128^(s-1-t),
+// peeled off from the least significant end with d_t in [-64, 63] (t > 0) and the carry into the next digit; the top digit
+// is in [-64, 64].  This is the same number as the round-to-nearest expansion of oz_split_kernel (a different, equally exact
+// signed-digit string when a remainder is exactly one half).
+constexpr int OZ_FUSED_MAX_SLICES = 9;
+constexpr int OZF_ROWS = 16, OZF_KB = 256, OZF_THREADS = 256;      // 16 rows x 16 chunks of 16 k per block of the k loop
+
+template <bool KCONTIG>
+__global__ void __launch_bounds__(OZF_THREADS, 2) oz_split_fused_kernel(const double *__restrict__ X, int64_t rows, int64_t k,
+                                                                        int64_t ld, int slices, int64_t rt_count, int64_t kc_count,
+                                                                        double *__restrict__ scale, uint8_t *__restrict__ digits) {
+    // KCONTIG: element (r, kk) = X[r * ld + kk], tile in shared memory [row][OZF_KB + 1]
+    // else:    element (r, kk) = X[kk * ld + r], tile in shared memory [kk][OZF_ROWS]
+    __shared__ double sx[OZF_ROWS * (OZF_KB + 1)];
+    __shared__ double red[OZF_THREADS / OZF_ROWS][OZF_ROWS];
+    __shared__ double s_mul[OZF_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rr = tid % OZF_ROWS, cc = tid / OZF_ROWS;               // row of the CTA / k lane (0..15)
+    const int64_t r0 = (int64_t)blockIdx.x * OZF_ROWS;
+    // ---- phase 1: max |x| of every row (independent loads, 8 in flight per thread)
+    if (KCONTIG) {
+#pragma unroll
+        for (int j = 0; j < OZF_ROWS / 8; ++j) {
+            const int lr = warp + 8 * j;
+            double m = 0.0;
+            if (r0 + lr < rows) {
+                const double *x = X + (r0 + lr) * ld;
+                int64_t i = lane;
+                for (; i + 7 * 32 < k; i += 8 * 32) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = x[i + 32 * u];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) m = fmax(m, fabs(v[u]));
+                }
+                for (; i < k; i += 32) m = fmax(m, fabs(x[i]));
+            }
+            m = warp_max(m);
+            if (lane == 0) red[0][lr] = m;
+        }
+        __syncthreads();
+    } else {
+        double m = 0.0;
+        if (r0 + rr < rows) {
+            const double *x = X + r0 + rr;
+            int64_t kk = cc;
+            for (; kk + 7 * 16 < k; kk += 8 * 16) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = x[(kk + 16 * u) * ld];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) m = fmax(m, fabs(v[u]));
+            }
+            for (; kk < k; kk += 16) m = fmax(m, fabs(x[kk * ld]));
+        }
+        red[cc][rr] = m;
+        __syncthreads();
+        if (tid < OZF_ROWS) {
+#pragma unroll
+            for (int j = 1; j < OZF_THREADS / OZF_ROWS; ++j) m = fmax(m, red[j][tid]);
+            red[0][tid] = m;
+        }
+        __syncthreads();
+    }
+    if (tid < OZF_ROWS) {
+        const unsigned long long mb = (unsigned long long)__double_as_longlong(red[0][tid]);
+        int be = (int)((mb >> 52) & 0x7ff);                          // biased exponent of the row maximum
+        be = min(max(be, 64), 1980);                                 // keep 2^e, 2^-e and their products finite normals
+        double sc = 1.0, mul = 0.0;
+        if (mb != 0ull) {
+            sc = __longlong_as_double((long long)(be + 1) << 52);    // 2^e, e = be - 1022: |x| 2^-e < 1
+            mul = __longlong_as_double((long long)(2051 - be + 7 * (slices - 1)) << 52);   // 2^(-e + 6 + 7 (s-1))
+        }
+        s_mul[tid] = mul;
+        scale[r0 + tid] = sc;                                        // the grid covers exactly the padded rows
+    }
+    __syncthreads();
+    // ---- phase 2: digits, 256 k at a time
+    const double mul = s_mul[rr];
+    const int64_t r = r0 + rr;
+    const int64_t rt = r / OZ_TILE, rin = r % OZ_TILE;
+    const int64_t kpad = kc_count * 16;
+    for (int64_t kb = 0; kb < kpad; kb += OZF_KB) {
+        if (KCONTIG) {
+#pragma unroll
+            for (int j = 0; j < OZF_ROWS / 8; ++j) {
+                const int lr = warp + 8 * j;
+                const bool rok = r0 + lr < rows;
+                const double *x = X + (r0 + lr) * ld + kb;
+#pragma unroll
+                for (int i = 0; i < OZF_KB / 32; ++i) {
+                    const int kk = lane + 32 * i;
+                    sx[lr * (OZF_KB + 1) + kk] = (rok && kb + kk < k) ? x[kk] : 0.0;
+                }
+            }
+        } else {
+            const bool rok = r0 + rr < rows;
+#pragma unroll
+            for (int j = 0; j < OZF_KB / 16; ++j) {
+                const int kk = cc + 16 * j;
+                sx[kk * OZF_ROWS + rr] = (rok && kb + kk < k) ? X[(kb + kk) * ld + r0 + rr] : 0.0;
+            }
+        }
+        __syncthreads();
+        const int64_t c = kb / 16 + cc;
+        if (c < kc_count) {
+            uint32_t packed[OZ_FUSED_MAX_SLICES][4];
+#pragma unroll
+            for (int t = 0; t < OZ_FUSED_MAX_SLICES; ++t) packed[t][0] = packed[t][1] = packed[t][2] = packed[t][3] = 0u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const double v = (KCONTIG ? sx[rr * (OZF_KB + 1) + cc * 16 + i] : sx[(cc * 16 + i) * OZF_ROWS + rr]) * mul;
+                long long xi = __double2ll_rn(v);
+#pragma unroll
+                for (int t = OZ_FUSED_MAX_SLICES - 1; t >= 1; --t) {
+                    if (t < slices) {
+                        const int d = (int)((xi + 64) & 127) - 64;
+                        xi = (xi - d) >> 7;
+                        packed[t][i >> 2] |= ((uint32_t)d & 0xffu) << (8 * (i & 3));
+                    }
+                }
+                packed[0][i >> 2] |= ((uint32_t)(int)xi & 0xffu) << (8 * (i & 3));
+            }
+#pragma unroll
+            for (int t = 0; t < OZ_FUSED_MAX_SLICES; ++t) {
+                if (t < slices) {
+                    uint8_t *dst = digits + (((int64_t)t * rt_count + rt) * kc_count + c) * OZ_CHUNK_BYTES + rin * 16;
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(packed[t][0], packed[t][1], packed[t][2], packed[t][3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- the tensor-core kernel ---------------------------------------------------------------------------------------------
 struct OzGemmArgs {
     const uint8_t *As, *Bs;      // digits of the split operands
@@ -152,12 +291,12 @@ struct OzGemmArgs {
     int32_t cps;                 // k chunks per pipeline stage (4 or 2)
     int32_t nstages;
     int32_t accumulate;          // 0: C = A.B, 1: C += A.B
-    int32_t acc_group;           // accumulators (diagonals) per pass: 4 or 2
     int32_t *abort_flag;
     long long *dbg;              // optional (B200_OZ_DEBUG): cycle counters of CTA 0, see b200_ozaki_mm_f64
 };
 
-constexpr int OZ_THREADS = 256;
+constexpr int OZ_THREADS = 384;             // warps 0-2: producer / MMA issuer / TMEM allocation, warps 4-11: epilogue
+constexpr int OZ_EPI_THREADS = 256;         // two warps per TMEM lane quarter, 64 columns of the 128 x 128 tile each
 constexpr int OZ_MAX_STAGES = 4;
 
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
@@ -167,17 +306,14 @@ __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
-    __shared__ uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint64_t full_bar[OZ_MAX_STAGES], empty_bar[OZ_MAX_STAGES], acc_full, acc_empty;
     __shared__ uint32_t tmem_slot;
     using namespace tc05;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = p.slices, cps = p.cps, nst = p.nstages;
     const uint32_t tile_bytes = (uint32_t)cps * OZ_CHUNK_BYTES;       // one slice tile of a stage
     const uint32_t stage_bytes = 2u * s * tile_bytes;
-    // accumulators per pass: 4 (all of TMEM, the epilogue and the next pass alternate) or 2 (two halves of TMEM, the epilogue
-    // of one half overlaps the MMAs of the other; more passes, i.e. more operand traffic)
-    const int G = p.acc_group;
-    const int npass = (s + G - 1) / G;
+    const int npass = (s + 3) / 4;
     const int ksteps = p.kc / cps;                                    // pipeline stages per pass
     const int mt_count = (p.M + OZ_TILE - 1) / OZ_TILE, nt_count = (p.N + OZ_TILE - 1) / OZ_TILE;
     const int ntiles = mt_count * nt_count;
@@ -187,10 +323,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128);
-        }
+        mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, OZ_EPI_THREADS);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(&tmem_slot, 512);
@@ -207,7 +341,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             const int mt = tile % mt_count, nt = tile / mt_count;
             for (int g = npass - 1; g >= 0 && ok; --g) {
-                const int nsl = s - G * (npass - 1 - g);             // slices 0 .. nsl-1 of both operands are needed (= d_hi + 1)
+                const int nsl = s - 4 * (npass - 1 - g);             // slices 0 .. nsl-1 of both operands are needed (= d_hi + 1)
                 for (int ks = 0; ks < ksteps; ++ks, ++it) {
                     const int slot = it % nst;
                     const long long tw = clock64();
@@ -237,12 +371,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         long long t_full = 0, t_acc = 0, t0 = clock64();
         for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
-                const int d_hi = s - 1 - G * (npass - 1 - g), d_lo = max(0, d_hi - G + 1);
-                const int half = (G == 2) ? (int)(pass_it & 1u) : 0;           // which set of accumulators
-                const uint32_t use = (G == 2) ? (pass_it >> 1) : pass_it;       // how often this set has been used before
-                const uint32_t tbase = tmem + (uint32_t)half * 2u * OZ_TILE;
+                const int d_hi = s - 1 - 4 * (npass - 1 - g), d_lo = max(0, d_hi - 3);
                 long long tw = clock64();
-                ok = mbar_wait(&acc_empty[half], (use & 1) ^ 1, p.abort_flag);   // epilogue has drained these accumulators
+                ok = mbar_wait(&acc_empty, (pass_it & 1) ^ 1, p.abort_flag);   // epilogue has drained the accumulators
                 t_acc += clock64() - tw;
                 if (!ok) break;
                 fence_after_sync();
@@ -259,7 +390,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                     const uint64_t da0 = oz_desc(sa), db0 = oz_desc(sa + (uint32_t)s * tile_bytes);
                     const uint32_t tile16 = tile_bytes >> 4, kstep16 = (2u * OZ_CHUNK_BYTES) >> 4;
                     for (int d = d_lo; d <= d_hi; ++d) {
-                        const uint32_t acc = tbase + (uint32_t)(d - d_lo) * OZ_TILE;
+                        const uint32_t acc = tmem + (uint32_t)(d - d_lo) * OZ_TILE;
                         for (int t = 0; t <= d; ++t) {                 // all pairs (t, u = d - t) of the diagonal
                             const uint64_t ad = da0 + (uint64_t)((uint32_t)t * tile16);
                             const uint64_t bd = db0 + (uint64_t)((uint32_t)(d - t) * tile16);
@@ -269,7 +400,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                     }
                     mma_commit(&empty_bar[slot]);                      // slot free once these MMAs have read it
                 }
-                if (ok) mma_commit(&acc_full[half]);                   // accumulators of this pass complete
+                if (ok) mma_commit(&acc_full);                         // accumulators of this pass complete
             }
         }
         if (p.dbg && blockIdx.x == 0) {
@@ -279,7 +410,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
         }
     } else if (warp >= 4) {
         // ================= epilogue: TMEM -> FP64 -> C =================
-        const int q = warp - 4;                                        // TMEM lane quarter = warp id % 4
+        const int q = warp & 3;                                        // TMEM lane quarter = warp id % 4
+        const int chalf = (warp - 4) >> 2;                             // columns [64 chalf, 64 chalf + 64) of the tile
         uint32_t pass_it = 0;
         bool ok = true;
         long long t_wait = 0, t0 = clock64();
@@ -287,12 +419,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
             const int mt = tile % mt_count, nt = tile / mt_count;
             const double *sbp = p.sB + (int64_t)nt * OZ_TILE;
             for (int g = npass - 1; g >= 0 && ok; --g, ++pass_it) {
-                const int d_hi = s - 1 - G * (npass - 1 - g), d_lo = max(0, d_hi - G + 1);
-                const int half = (G == 2) ? (int)(pass_it & 1u) : 0;           // which set of accumulators
-                const uint32_t use = (G == 2) ? (pass_it >> 1) : pass_it;       // how often this set has been used before
-                const uint32_t tbase = tmem + (uint32_t)half * 2u * OZ_TILE;
+                const int d_hi = s - 1 - 4 * (npass - 1 - g), d_lo = max(0, d_hi - 3);
                 const long long tw = clock64();
-                ok = mbar_wait(&acc_full[half], use & 1, p.abort_flag);
+                ok = mbar_wait(&acc_full, pass_it & 1, p.abort_flag);
                 t_wait += clock64() - tw;
                 if (!ok) break;
                 fence_after_sync();
@@ -301,16 +430,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                 const bool add = (g != npass - 1) || p.accumulate;
                 const int row0 = mt * OZ_TILE + q * 32;                // the 32 rows of this warp
                 const double sa_l = p.sA[row0 + lane];                 // scale of this lane's row (sA is padded to whole tiles)
-                for (int c0 = 0; c0 < OZ_TILE; c0 += 32) {
+                for (int c0 = 64 * chalf; c0 < 64 * chalf + 64; c0 += 32) {
                     double h[32];
                     uint32_t r[32];
-                    tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(d_hi - d_lo) * OZ_TILE + c0, r);
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d_hi - d_lo) * OZ_TILE + c0, r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         h[j] = __hiloint2double(0x43300000, (int)(r[j] ^ 0x80000000u)) - 4503601774854144.0;
                     for (int d = d_hi - 1; d >= d_lo; --d) {
-                        tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(d - d_lo) * OZ_TILE + c0, r);
+                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d - d_lo) * OZ_TILE + c0, r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -342,12 +471,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                     double *cp = p.C + (int64_t)row0 * p.ldc + col;
                     if (col < p.N) {
                         if (add) {
-                            double old[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) old[j] = (row0 + j < p.M) ? cp[(int64_t)j * p.ldc] : 0.0;
+                            for (int j0 = 0; j0 < 32; j0 += 16) {       // 16 row segments in flight (register budget)
+                                double old[16];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (row0 + j < p.M) cp[(int64_t)j * p.ldc] = fma(h[j], wsb, old[j]);
+                                for (int j = 0; j < 16; ++j) old[j] = (row0 + j0 + j < p.M) ? cp[(int64_t)(j0 + j) * p.ldc] : 0.0;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (row0 + j0 + j < p.M) cp[(int64_t)(j0 + j) * p.ldc] = fma(h[j0 + j], wsb, old[j]);
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
@@ -356,7 +488,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
                     }
                 }
                 fence_before_sync();
-                mbar_arrive(&acc_empty[half]);
+                mbar_arrive(&acc_empty);
             }
         }
         if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) {
@@ -369,6 +501,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmArgs p) {
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+const bool g_split_fused = getenv("B200_OZ_SPLIT2") == nullptr;   // B200_OZ_SPLIT2=1: the two-pass split kernels (A/B)
 int *g_abort_flag = nullptr;   // device int: raised by a wait that timed out (never in a correct run)
 int g_abort_dev = -1;
 
@@ -407,6 +540,15 @@ extern "C" int b200_ozaki_split_f64(int64_t rows, int64_t k, const double *X, in
     uint8_t *base = static_cast<uint8_t *>(out_dev);
     double *scale = reinterpret_cast<double *>(base + L.scale_off);
     unsigned long long *maxbits = reinterpret_cast<unsigned long long *>(base + L.max_off);
+    if (slices <= OZ_FUSED_MAX_SLICES && g_split_fused) {
+        const unsigned nblk = (unsigned)(L.rt * OZ_TILE / OZF_ROWS);
+        if (ld_k == 1)
+            oz_split_fused_kernel<true><<<nblk, OZF_THREADS, 0, st>>>(X, rows, k, ld_row, slices, L.rt, L.kc, scale, base);
+        else
+            oz_split_fused_kernel<false><<<nblk, OZF_THREADS, 0, st>>>(X, rows, k, ld_k, slices, L.rt, L.kc, scale, base);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
     if (ld_k == 1) {
         int rows_per_block = 8;
         oz_rowmax_kcontig_kernel<<<(unsigned)((rows + rows_per_block - 1) / rows_per_block), 32 * rows_per_block, 0, st>>>(
@@ -463,8 +605,6 @@ extern "C" int b200_ozaki_mm_f64(int64_t m, int64_t n, int64_t k, int32_t slices
     }
     // pipeline shape: as many k chunks per stage as leave at least two stages in shared memory
     static const int force_cps = getenv("B200_OZ_CPS") ? atoi(getenv("B200_OZ_CPS")) : 0;   // tuning knob (2 or 4)
-    static const int force_acc = getenv("B200_OZ_ACC") ? atoi(getenv("B200_OZ_ACC")) : 0;   // tuning knob (2 or 4)
-    p.acc_group = force_acc == 2 ? 2 : 4;
     p.cps = force_cps == 2 ? 2 : 4;
     int64_t stage = 2LL * slices * p.cps * OZ_CHUNK_BYTES;
     if (OZ_SMEM_BUDGET / stage < 2) {

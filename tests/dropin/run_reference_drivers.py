@@ -42,6 +42,14 @@ def setup(mode):
     return dropin
 
 
+def _spectrum_summary(psi):
+    """bond dimensions and -- robust against the rounding noise of a cut at `svd_min` -- the number of Schmidt values that are
+    two orders of magnitude above it"""
+    import numpy as np
+    return {'chi': [int(c) for c in psi.chi],
+            'n_schmidt_above_1e-8': [int(np.sum(np.asarray(psi.get_SL(i)) > 1.e-8)) for i in range(1, psi.L)]}
+
+
 def case_tfi_dmrg(dropin):
     """config 0: examples/d_dmrg.py TFIChain L=20 chi=50 two-site DMRG (E = -25.1077971116238)"""
     from tenpy.models.tf_ising import TFIChain
@@ -51,7 +59,7 @@ def case_tfi_dmrg(dropin):
     psi = MPS.from_product_state(M.lat.mps_sites(), ['up'] * 20, bc='finite')
     info = dmrg.run(psi, M, {'mixer': None, 'max_E_err': 1.e-10, 'trunc_params': {'chi_max': 50, 'svd_min': 1.e-10},
                              'combine': True})
-    return {'E': float(info['E']), 'S_mid': float(psi.entanglement_entropy()[9]), 'chi': [int(c) for c in psi.chi]}
+    return dict(E=float(info['E']), S_mid=float(psi.entanglement_entropy()[9]), **_spectrum_summary(psi))
 
 
 def case_xxz_dmrg_mixer(dropin):
@@ -65,7 +73,7 @@ def case_xxz_dmrg_mixer(dropin):
     info = dmrg.run(psi, M, {'mixer': True, 'mixer_params': {'amplitude': 1.e-5, 'decay': 2., 'disable_after': 6},
                              'max_E_err': 1.e-11, 'max_S_err': 1.e-8, 'max_sweeps': 20, 'combine': True,
                              'trunc_params': {'chi_max': 60, 'svd_min': 1.e-10}})
-    return {'E': float(info['E']), 'S_mid': float(psi.entanglement_entropy()[L // 2 - 1]), 'chi': [int(c) for c in psi.chi]}
+    return dict(E=float(info['E']), S_mid=float(psi.entanglement_entropy()[L // 2 - 1]), **_spectrum_summary(psi))
 
 
 def case_tfi_dmrg_fast_engine(dropin):
@@ -82,7 +90,7 @@ def case_tfi_dmrg_fast_engine(dropin):
     eng = Engine(psi, M, {'mixer': None, 'max_E_err': 1.e-10, 'trunc_params': {'chi_max': 50, 'svd_min': 1.e-10},
                           'combine': True})
     E, _ = eng.run()
-    return {'E': float(E), 'S_mid': float(psi.entanglement_entropy()[9]), 'chi': [int(c) for c in psi.chi]}
+    return dict(E=float(E), S_mid=float(psi.entanglement_entropy()[9]), **_spectrum_summary(psi))
 
 
 def case_tfi_tebd_imag(dropin):
@@ -97,7 +105,7 @@ def case_tfi_tebd_imag(dropin):
                                    'trunc_params': {'chi_max': 20, 'svd_min': 1.e-10}})
     eng.run_GS()
     E = M.bond_energies(psi)
-    return {'E': float(sum(E)), 'S_mid': float(psi.entanglement_entropy()[L // 2 - 1]), 'chi': [int(c) for c in psi.chi]}
+    return dict(E=float(sum(E)), S_mid=float(psi.entanglement_entropy()[L // 2 - 1]), **_spectrum_summary(psi))
 
 
 def _tebd_models():

