@@ -229,7 +229,9 @@ int b200_svd_set_deflation(int on);
  * 3 = jacobi_eig_kernel_v3 (G and Q in registers, warp shuffles, two barriers per set); returns the old value */
 int b200_svd_set_eig_variant(int variant);
 /* inner sweeps of the version-3 pivot eigen-solver (1..16, default 2): profiles/jacobi_sweeps_study.md finds the number
- * of outer sweeps unchanged between 2 and 4; returns the old value */
+ * of outer sweeps unchanged between 2 and 4.  0 = "cross" mode: one pass over the pairs between the two row blocks of a
+ * pivot only, the pairs inside a block once per outer sweep (the element-wise cyclic sweep in block order).  Returns the
+ * old value */
 int b200_svd_set_eig_inner_sweeps(int n);
 /* additional deflation threshold relative to |A_i|_F (default 0 = rounding level only): directions with a
  * singular value below tol_rel*|A_i|_F are treated like the negligible ones; returns the old value.  A DMRG

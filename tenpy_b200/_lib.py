@@ -213,6 +213,7 @@ class DeviceLib:
             raise B200Error('no CUDA device visible: tenpy_b200 computes on a B200 only (no CPU fallback)')
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.profile = None   # set to {} to collect CUDA-event timings per kernel family
+        self._stream = None
 
     def profile_summary(self):
         """{family: (n_calls, total_ms)} of the collected event pairs; synchronises."""
@@ -230,7 +231,16 @@ class DeviceLib:
 
     # -- plumbing
     def stream(self):
-        return c_vp(self.torch.cuda.current_stream().cuda_stream)
+        """the CUDA stream every kernel of this library handle is enqueued on: torch's current stream at the time of the first
+        call (looking it up costs ~10 us of Python per launch, 28 000 times per benchmark sweep); code that switches torch's
+        current stream calls :meth:`refresh_stream` afterwards."""
+        st = self._stream
+        if st is None:
+            st = self._stream = c_vp(self.torch.cuda.current_stream().cuda_stream)
+        return st
+
+    def refresh_stream(self):
+        self._stream = None
 
     def _check(self, rc):
         if rc != 0:

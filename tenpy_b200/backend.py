@@ -39,6 +39,7 @@ def use_library(lib):
     if npc is not None:
         npc._PLAN_CACHE.clear()
         npc._EMPTY_LAYOUTS.clear()
+        npc._SMALL_DEV_CACHE.clear()
     return lib
 
 

@@ -694,6 +694,11 @@ extern "C" int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m, const in
         scratch_dev = dev;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    static cudaStream_t scratch_stream = nullptr;
+    static bool scratch_used = false;
+    if (scratch_used && scratch_stream != st) B200_CUDA_CHECK(cudaStreamSynchronize(scratch_stream));
+    scratch_stream = st;
+    scratch_used = true;
     DeviceGemmDesc d;
     d.device = dev;
     char *at = scratch;
@@ -717,12 +722,10 @@ extern "C" int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m, const in
     for (auto &p : pairs)
         if ((p.k & 1) || (p.a_off & 1) || (p.b_off & 1)) vec = false;
     d.vec = vec;
-    int rc = run_desc(d, A, B, C, st);
-    if (rc == B200_OK) {
-        cudaError_t e = cudaStreamSynchronize(st);   // host staging vectors and the scratch are reused afterwards
-        if (e != cudaSuccess) rc = set_error(B200_ERR_CUDA, "grouped gemm failed: %s", cudaGetErrorString(e));
-    }
-    return rc;
+    // No host synchronisation: the pageable staging vectors are consumed by cudaMemcpyAsync before it returns, and the next
+    // call's copies into `scratch` are ordered behind this call's kernels as long as both use the same stream (a call on
+    // another stream waits for the previous one first, see above).
+    return run_desc(d, A, B, C, st);
 }
 
 // ---- misc ABI ------------------------------------------------------------------------------------

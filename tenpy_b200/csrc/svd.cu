@@ -409,7 +409,7 @@ __device__ __forceinline__ int jeig3_partner(int x, int step) {
 __global__ void __launch_bounds__(JTHREADS)
     jacobi_eig_kernel_v3(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
                          const int *__restrict__ done, double tol_scale, const double *__restrict__ Gbuf, int nsplit,
-                         double *__restrict__ QTbuf, int *__restrict__ flags, int inner_sweeps) {
+                         double *__restrict__ QTbuf, int *__restrict__ flags, int inner_sweeps, int round) {
     __shared__ double sA[JP * JLDG];
     __shared__ double sT[JP * JLDG];
     __shared__ double red[32];
@@ -462,10 +462,19 @@ __global__ void __launch_bounds__(JTHREADS)
     if (tid == 0) atomicAdd(&rot_count[mi], 1);
 
     const double tol_in = 1e-15;
+    // inner_sweeps == 0 ("cross" mode): one pass over the 16 x 16 pairs BETWEEN the two row blocks only (16 rotation sets
+    // instead of 31 per pass); the pairs inside a block are rotated once per outer sweep, in the round in which every block
+    // of the matrix is paired (round % (nb_act - 1) == 0: one full pass there).  Together: the cyclic element-wise Jacobi
+    // sweep in block order, every pair of rows rotated exactly once per outer sweep.
+    const int nr_blk = mt.nb_act - 1;
+    const bool cross = inner_sweeps == 0 && nr_blk > 1 && (round % nr_blk) != 0;
+    const int nsteps = cross ? JB : JP - 1;
+    if (inner_sweeps == 0) inner_sweeps = 1;
     for (int sweep = 0; sweep < inner_sweeps; ++sweep) {
-        for (int step = 0; step < JP - 1; ++step) {
+        for (int step = 0; step < nsteps; ++step) {
             // 1. rotation of the pair that contains row index `lane`
-            const int partner = jeig3_partner(lane, step);
+            const int partner = cross ? (lane < JB ? JB + ((lane + step) & (JB - 1)) : ((lane - JB - step) & (JB - 1)))
+                                      : jeig3_partner(lane, step);
             const bool is_p = lane < partner;
             const int p = is_p ? lane : partner, q = is_p ? partner : lane;
             const double gpp = sA[p * JLDG + p], gqq = sA[q * JLDG + q], gpq = sA[p * JLDG + q];
@@ -833,7 +842,7 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
             B200_CHECK_LAUNCH();
             if (g_eig_variant == 3)
                 jacobi_eig_kernel_v3<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit,
-                                                               d_QT, d_flags, g_eig_inner_sweeps);
+                                                               d_QT, d_flags, g_eig_inner_sweeps, round_counter);
             else
                 jacobi_eig_kernel<<<n_cta, JTHREADS, 0, st>>>(d_mats, d_cta, d_rot, d_done, tol_scale, d_G, nsplit, d_QT,
                                                             d_flags);
@@ -953,7 +962,7 @@ extern "C" int b200_svd_set_eig_variant(int variant) {
 
 extern "C" int b200_svd_set_eig_inner_sweeps(int n) {
     int old = g_eig_inner_sweeps;
-    if (n >= 1 && n <= 16) g_eig_inner_sweeps = n;
+    if (n >= 0 && n <= 16) g_eig_inner_sweeps = n;   // 0: cross mode of version 3 (see jacobi_eig_kernel_v3)
     return old;
 }
 

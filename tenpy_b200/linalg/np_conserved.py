@@ -1562,15 +1562,32 @@ class _CompletionFailed(Exception):
     pass
 
 
+_SMALL_DEV_CACHE = {}     # small constant device arrays (copy records, index lists, the scalar 1.) by content
+
+
+def _dev_const(key, make):
+    """device copy of a small constant host array, made once (every host->device copy of a record is a driver call)"""
+    ent = _SMALL_DEV_CACHE.get(key)
+    if ent is None or ent[0] is not backend.get_lib():
+        if len(_SMALL_DEV_CACHE) > 4096:
+            _SMALL_DEV_CACHE.clear()
+        host = make()
+        ent = _SMALL_DEV_CACHE[key] = (backend.get_lib(), host, backend.to_device(host))
+    return ent[1], ent[2]
+
+
 def _strided_copy(lib, src, soff, dst, doff, shape, sstride, dstride):
-    rec = np.zeros((1, 22), dtype=np.int64)
-    r = len(shape)
-    rec[0, 0], rec[0, 1], rec[0, 2], rec[0, 3] = soff, doff, int(np.prod(shape)), r
-    rec[0, 4:10] = 1
-    rec[0, 4:4 + r] = shape
-    rec[0, 10:10 + r] = sstride
-    rec[0, 16:16 + r] = dstride
-    lib.copy_blocks(rec, backend.to_device(rec), src, dst)
+    def make():
+        rec = np.zeros((1, 22), dtype=np.int64)
+        r = len(shape)
+        rec[0, 0], rec[0, 1], rec[0, 2], rec[0, 3] = soff, doff, int(np.prod(shape)), r
+        rec[0, 4:10] = 1
+        rec[0, 4:4 + r] = shape
+        rec[0, 10:10 + r] = sstride
+        rec[0, 16:16 + r] = dstride
+        return rec
+    rec, rec_dev = _dev_const(('copy', soff, doff, tuple(shape), tuple(sstride), tuple(dstride)), make)
+    lib.copy_blocks(rec, rec_dev, src, dst)
 
 
 def _gemm(lib, mm, nn, kk, A, B, C):
@@ -1584,7 +1601,7 @@ def _null_space_completion(lib, V, r, p, kf):
     smallest leverage (so that ``X0 X0^T = 1 - C^T C`` is well conditioned), then orthonormalise with
     Newton-Schulz iterations ``X <- (1 - D/2) X``, ``D = X X^T - 1`` -- GEMMs only (grouped FP64 tensor-core
     kernel).  Left multiplications keep the rows inside the orthogonal complement of `V`."""
-    ones = backend.to_device(np.ones(1))
+    ones = _dev_const('one', lambda: np.ones(1))[1]
     X = backend.zeros(kf * p)
     if r > 0:
         lev = backend.empty(p)
@@ -1605,8 +1622,9 @@ def _null_space_completion(lib, V, r, p, kf):
         lib.axpy_segments(len(part), backend.to_device(part), 1, 1., ones, X)
     if r == 0:
         return X
-    dseg = np.stack([np.zeros(kf, np.int64), np.arange(kf, dtype=np.int64) * (kf + 1), np.ones(kf, np.int64)], axis=1)
-    dseg_dev = [backend.to_device(np.ascontiguousarray(dseg[s0:s0 + 32768])) for s0 in range(0, kf, 32768)]
+    dseg_dev = [_dev_const(('diag', kf, s0), lambda s0=s0: np.ascontiguousarray(np.stack(
+        [np.zeros(kf, np.int64), np.arange(kf, dtype=np.int64) * (kf + 1), np.ones(kf, np.int64)], axis=1)[s0:s0 + 32768]))[1]
+        for s0 in range(0, kf, 32768)]
     XT = backend.empty(kf * p)
     G = backend.empty(kf * kf)
     DX = backend.empty(kf * p)

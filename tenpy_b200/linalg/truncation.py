@@ -209,9 +209,15 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
     if res is not None:
         U, S, VH, lost = res
     else:
+        # how many singular triplets the truncation below can keep at most: chi_max; none of the deflated directions (values
+        # <= tol |theta|) if they are below `svd_min` anyway -- then their vectors need no orthonormal completion
+        n_keep = chi_max
+        svd_min, chi_min = trunc_par.get('svd_min', 1.e-14), trunc_par.get('chi_min', None)
+        if svd_min and 0. < tol <= svd_min and not (chi_min and chi_min > 1):
+            n_keep = 0
         U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR,
                            inner_labels=inner_labels, guess=guess, deflation_tol=tol,
-                           n_keep=(chi_max if full_out is None else None))
+                           n_keep=(n_keep if full_out is None else None))
     if full_out is not None:
         full_out.append((U.copy(deep=False), VH.copy(deep=False)))
     renormalization = np.sqrt(np.sum(S**2) + lost**2)
