@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -701,7 +702,13 @@ __global__ void __launch_bounds__(128)
 // profiles/r02/r02g_svd_variants.jsonl) but the numerically low-rank two-site wave functions of a converged DMRG then
 // need 14 instead of 11 outer sweeps (svd family of the benchmark sweep 718 -> 819 ms, r02h): the default stays 2.
 static int g_eig_variant = 3;
-static int g_eig_inner_sweeps = J_INNER_SWEEPS;   // inner sweeps of version 3 (version 1: fixed J_INNER_SWEEPS)
+static int env_inner_sweeps() {                     // B200_SVD_INNER=0..16 overrides the default (A/B runs of whole sweeps)
+    const char *e = getenv("B200_SVD_INNER");
+    if (e == nullptr || *e == 0) return J_INNER_SWEEPS;
+    const int n = atoi(e);
+    return (n >= 0 && n <= 16) ? n : J_INNER_SWEEPS;
+}
+static int g_eig_inner_sweeps = env_inner_sweeps();   // inner sweeps of version 3 (0: cross mode; version 1: fixed J_INNER_SWEEPS)
 struct JLayout {
     std::vector<JMat> mats;
     std::vector<int> cta_mat;
