@@ -233,6 +233,11 @@ int b200_svd_set_eig_variant(int variant);
  * pivot only, the pairs inside a block once per outer sweep (the element-wise cyclic sweep in block order).  Returns the
  * old value */
 int b200_svd_set_eig_inner_sweeps(int n);
+/* small-block regime of the block SVD / eigh: while the longest row (columns of Y, rows of W) of the matrices still being
+ * iterated is <= max_ld, a Jacobi round is ONE launch (jacobi_round_fused_kernel: Gram matrix, pivot eigen-solver and
+ * both applications back to back in the CTA of the pair) instead of three with column splits.  Default 512
+ * (environment B200_SVD_FUSED_LD); 0 switches the regime off.  Returns the old value */
+int b200_svd_set_fused_max_ld(int max_ld);
 /* additional deflation threshold relative to |A_i|_F (default 0 = rounding level only): directions with a
  * singular value below tol_rel*|A_i|_F are treated like the negligible ones; returns the old value.  A DMRG
  * truncation discards them anyway (the reference's `svd_min`, truncation.py:196). */

@@ -75,6 +75,7 @@ _SIGNATURES = {
     'b200_svd_set_deflation': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_eig_variant': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_eig_inner_sweeps': (ctypes.c_int, [ctypes.c_int]),
+    'b200_svd_set_fused_max_ld': (ctypes.c_int, [ctypes.c_int]),
     'b200_svd_set_deflation_tol': (c_f64, [c_f64]),
     'b200_block_svd_worksize': (c_i64, [c_i64, c_i64p, c_i64p]),
     'b200_block_svd_f64': (ctypes.c_int, [c_i64, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_vp, c_vp, c_vp,
@@ -402,6 +403,10 @@ class DeviceLib:
     def svd_set_eig_inner_sweeps(self, n):
         """inner sweeps of jacobi_eig_kernel_v2 (default 4); returns the old value"""
         return int(self.c.b200_svd_set_eig_inner_sweeps(int(n)))
+
+    def svd_set_fused_max_ld(self, max_ld):
+        """row-length limit of the single-launch Jacobi rounds (0: off); returns the old value"""
+        return int(self.c.b200_svd_set_fused_max_ld(int(max_ld)))
 
     def svd_set_eig_variant(self, variant):
         """1 = jacobi_eig_kernel (default), 2 = jacobi_eig_kernel_v2; returns the old value"""

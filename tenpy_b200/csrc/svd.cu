@@ -152,23 +152,23 @@ __device__ __forceinline__ bool j_pair_rows(const JMat &mt, int j, int round, co
 //   jacobi_eig_kernel   grid (pairs): convergence test, parallel cyclic Jacobi on G in shared memory, Q^T (rows
 //                       ordered by descending eigenvalue) -> QTbuf[pair], flag[pair] = rotated
 //   jacobi_apply_kernel grid (nsplit, pairs, 2): P <- Q^T P (z = 0) and the same rows of W <- Q^T W (z = 1)
-__global__ void __launch_bounds__(JTHREADS)
-    jacobi_gram_kernel(const double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
-                       const int *__restrict__ rmap, int round, const int *__restrict__ done,
-                       double *__restrict__ Gbuf) {
-    extern __shared__ __align__(16) double jsmem[];
-    double *bufs = jsmem;   // 2 * JP * JLDP
+// (the three phases are device functions so that jacobi_round_fused_kernel can run them back to back in one launch; buffers
+// one phase writes and the next one reads -- Gbuf, QTbuf, flags, work -- are deliberately NOT const __restrict__ there: the
+// read-only data path is not coherent with writes of the same kernel)
+__device__ __forceinline__ void jacobi_gram_body(double *bufs, const double *work, const JMat *__restrict__ mats,
+                                                 const int *__restrict__ cta_mat, const int *__restrict__ rmap, int round,
+                                                 const int *__restrict__ done, double *Gbuf, int split, int nsplit, int pair) {
     __shared__ int s_rows[JP];
-    const int mi = cta_mat[blockIdx.y];
+    const int mi = cta_mat[pair];
     if (done[mi]) return;
     const JMat mt = mats[mi];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    if (!j_pair_rows(mt, blockIdx.y - mt.cta_begin, round, rmap, s_rows, tid)) return;
+    if (!j_pair_rows(mt, pair - mt.cta_begin, round, rmap, s_rows, tid)) return;
     __syncthreads();
     const double *Y = work + mt.y_off;
     const int ld = mt.ldy;
     const int nch = (ld + JKC - 1) / JKC;
-    const int ch0 = blockIdx.x, chstep = gridDim.x;
+    const int ch0 = split, chstep = nsplit;
     if (ch0 >= nch) return;
     const int tm = warp >> 2, tn = warp & 3;  // 2 x 4 tiles of 16 x 8
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -197,13 +197,21 @@ __global__ void __launch_bounds__(JTHREADS)
         __syncthreads();
     }
     cp_async_wait<0>();
-    // partial result of this column split (summed in a fixed order by jacobi_eig_kernel: deterministic)
-    double *G = Gbuf + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (JP * JP);
+    // partial result of this column split (summed in a fixed order by the eigen-solver phase: deterministic)
+    double *G = Gbuf + ((int64_t)pair * nsplit + split) * (JP * JP);
     const int r0 = tm * 16 + g, c0 = tn * 8 + 2 * t;
     G[r0 * JP + c0] = acc[0];
     G[r0 * JP + c0 + 1] = acc[1];
     G[(r0 + 8) * JP + c0] = acc[2];
     G[(r0 + 8) * JP + c0 + 1] = acc[3];
+}
+
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_gram_kernel(const double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
+                       const int *__restrict__ rmap, int round, const int *__restrict__ done,
+                       double *__restrict__ Gbuf) {
+    extern __shared__ __align__(16) double jsmem[];
+    jacobi_gram_body(jsmem, work, mats, cta_mat, rmap, round, done, Gbuf, blockIdx.x, gridDim.x, blockIdx.y);
 }
 
 __global__ void __launch_bounds__(JTHREADS)
@@ -407,26 +415,26 @@ __device__ __forceinline__ int jeig3_partner(int x, int step) {
     return y;
 }
 
-__global__ void __launch_bounds__(JTHREADS)
-    jacobi_eig_kernel_v3(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
-                         const int *__restrict__ done, double tol_scale, const double *__restrict__ Gbuf, int nsplit,
-                         double *__restrict__ QTbuf, int *__restrict__ flags, int inner_sweeps, int round) {
+__device__ __forceinline__ void jacobi_eig_v3_body(const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
+                                                   int *rot_count, const int *__restrict__ done, double tol_scale,
+                                                   const double *Gbuf, int nsplit, double *QTbuf, int *flags, int inner_sweeps,
+                                                   int round, int pair) {
     __shared__ double sA[JP * JLDG];
     __shared__ double sT[JP * JLDG];
     __shared__ double red[32];
     __shared__ int s_rank[JP];
     __shared__ int s_any;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) flags[blockIdx.x] = 0;
-    const int mi = cta_mat[blockIdx.x];
+    if (tid == 0) flags[pair] = 0;
+    const int mi = cta_mat[pair];
     if (done[mi]) return;
     const JMat mt = mats[mi];
-    if (2 * (blockIdx.x - mt.cta_begin) >= mt.nb_act) return;
+    if (2 * (pair - mt.cta_begin) >= mt.nb_act) return;
     double g[4], qv[4];
     {
         const int nch = (mt.ldy + JKC - 1) / JKC;
         const int ns = nsplit < nch ? nsplit : nch;
-        const double *G = Gbuf + (int64_t)blockIdx.x * nsplit * (JP * JP);
+        const double *G = Gbuf + (int64_t)pair * nsplit * (JP * JP);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int c = 4 * warp + i;
@@ -527,27 +535,32 @@ __global__ void __launch_bounds__(JTHREADS)
         s_rank[tid] = rk;
     }
     __syncthreads();
-    double *QT = QTbuf + (int64_t)blockIdx.x * (JP * JP);
+    double *QT = QTbuf + (int64_t)pair * (JP * JP);
     // QT[rank[i]][k] = Q[k][i]; this thread holds Q[4w+j][lane]
 #pragma unroll
     for (int i = 0; i < 4; ++i) QT[s_rank[lane] * JP + 4 * warp + i] = qv[i];
-    if (tid == 0) flags[blockIdx.x] = 1;
+    if (tid == 0) flags[pair] = 1;
 }
 
 __global__ void __launch_bounds__(JTHREADS)
-    jacobi_apply_kernel(double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
-                        const int *__restrict__ rmap, int round, const double *__restrict__ QTbuf,
-                        const int *__restrict__ flags) {
-    extern __shared__ __align__(16) double jsmem[];
-    double *bufs = jsmem;   // 2 * JP * JLDP
+    jacobi_eig_kernel_v3(const JMat *__restrict__ mats, const int *__restrict__ cta_mat, int *__restrict__ rot_count,
+                         const int *__restrict__ done, double tol_scale, const double *__restrict__ Gbuf, int nsplit,
+                         double *__restrict__ QTbuf, int *__restrict__ flags, int inner_sweeps, int round) {
+    jacobi_eig_v3_body(mats, cta_mat, rot_count, done, tol_scale, Gbuf, nsplit, QTbuf, flags, inner_sweeps, round, blockIdx.x);
+}
+
+__device__ __forceinline__ void jacobi_apply_body(double *bufs, double *work, const JMat *__restrict__ mats,
+                                                  const int *__restrict__ cta_mat, const int *__restrict__ rmap, int round,
+                                                  const double *QTbuf, const int *flags, int split, int nsplit, int pair,
+                                                  int which) {
     __shared__ int s_rows[JP];
-    if (!flags[blockIdx.y]) return;
-    const int mi = cta_mat[blockIdx.y];
+    if (!flags[pair]) return;
+    const int mi = cta_mat[pair];
     const JMat mt = mats[mi];
     const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    if (!j_pair_rows(mt, blockIdx.y - mt.cta_begin, round, rmap, s_rows, tid)) return;
+    if (!j_pair_rows(mt, pair - mt.cta_begin, round, rmap, s_rows, tid)) return;
     __syncthreads();
-    const double *QT = QTbuf + (int64_t)blockIdx.y * (JP * JP);
+    const double *QT = QTbuf + (int64_t)pair * (JP * JP);
     double qa[2][4][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -559,10 +572,37 @@ __global__ void __launch_bounds__(JTHREADS)
             qa[i][k8][2] = ap[4];
             qa[i][k8][3] = ap[8 * JP + 4];
         }
-    if (blockIdx.z == 0)
-        j_apply(bufs, qa, work + mt.y_off, mt.ldy, s_rows, tid, blockIdx.x, gridDim.x);
+    if (which == 0)
+        j_apply(bufs, qa, work + mt.y_off, mt.ldy, s_rows, tid, split, nsplit);
     else
-        j_apply(bufs, qa, work + mt.w_off, mt.ldw, s_rows, tid, blockIdx.x, gridDim.x);
+        j_apply(bufs, qa, work + mt.w_off, mt.ldw, s_rows, tid, split, nsplit);
+}
+
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_apply_kernel(double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
+                        const int *__restrict__ rmap, int round, const double *__restrict__ QTbuf,
+                        const int *__restrict__ flags) {
+    extern __shared__ __align__(16) double jsmem[];
+    jacobi_apply_body(jsmem, work, mats, cta_mat, rmap, round, QTbuf, flags, blockIdx.x, gridDim.x, blockIdx.y, blockIdx.z);
+}
+
+// Small-block regime: one launch per round.  For matrices of a few hundred columns the three phases of a pair are a few
+// microseconds of streaming around the rotation chain of the pivot solver, and the launch boundaries between them cost as
+// much as the streaming itself; here one CTA per pair runs them back to back (no column split; G, Q^T and the flag go
+// through the same global buffers, ordered by the CTA barrier).
+__global__ void __launch_bounds__(JTHREADS)
+    jacobi_round_fused_kernel(double *work, const JMat *__restrict__ mats, const int *__restrict__ cta_mat,
+                              const int *__restrict__ rmap, int round, const int *__restrict__ done, int *rot_count,
+                              double tol_scale, double *Gbuf, double *QTbuf, int *flags, int inner_sweeps) {
+    extern __shared__ __align__(16) double jsmem[];
+    const int pair = blockIdx.x;
+    jacobi_gram_body(jsmem, work, mats, cta_mat, rmap, round, done, Gbuf, 0, 1, pair);
+    __syncthreads();
+    jacobi_eig_v3_body(mats, cta_mat, rot_count, done, tol_scale, Gbuf, 1, QTbuf, flags, inner_sweeps, round, pair);
+    __syncthreads();
+    jacobi_apply_body(jsmem, work, mats, cta_mat, rmap, round, QTbuf, flags, 0, 1, pair, 0);
+    __syncthreads();
+    jacobi_apply_body(jsmem, work, mats, cta_mat, rmap, round, QTbuf, flags, 0, 1, pair, 1);
 }
 
 // ---- init / finalize kernels ---------------------------------------------------------------------
@@ -702,6 +742,13 @@ __global__ void __launch_bounds__(128)
 // profiles/r02/r02g_svd_variants.jsonl) but the numerically low-rank two-site wave functions of a converged DMRG then
 // need 14 instead of 11 outer sweeps (svd family of the benchmark sweep 718 -> 819 ms, r02h): the default stays 2.
 static int g_eig_variant = 3;
+static int env_fused_max_ld() {                     // B200_SVD_FUSED_LD: largest row length of the single-launch rounds (0: off)
+    const char *e = getenv("B200_SVD_FUSED_LD");
+    if (e == nullptr || *e == 0) return 512;
+    const int n = atoi(e);
+    return n >= 0 ? n : 512;
+}
+static int g_fused_max_ld = env_fused_max_ld();
 static int env_inner_sweeps() {                     // B200_SVD_INNER=0..16 overrides the default (A/B runs of whole sweeps)
     const char *e = getenv("B200_SVD_INNER");
     if (e == nullptr || *e == 0) return J_INNER_SWEEPS;
@@ -811,6 +858,8 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
                                              jacobi_smem_bytes()));
         B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              jacobi_smem_bytes()));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             jacobi_smem_bytes()));
         attr_set = true;
     }
     std::vector<int> rot((size_t)nmat), done((size_t)nmat, 0);
@@ -843,7 +892,16 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
             }
         int nsplit = (3 * sm_count() + act_pairs - 1) / std::max(1, act_pairs);
         nsplit = std::max(1, std::min(nsplit, std::min(J_NSPLIT_MAX, (max_ld + JKC - 1) / JKC)));
+        // small-block regime: all phases of a round in one launch (one CTA per pair, no column split)
+        const bool fused = g_eig_variant == 3 && max_ld <= g_fused_max_ld;
         for (int r = 0; r < rounds; ++r) {
+            if (fused) {
+                jacobi_round_fused_kernel<<<n_cta, JTHREADS, jacobi_smem_bytes(), st>>>(
+                    wf, d_mats, d_cta, d_rmap, round_counter, d_done, d_rot, tol_scale, d_G, d_QT, d_flags, g_eig_inner_sweeps);
+                B200_CHECK_LAUNCH();
+                ++round_counter;
+                continue;
+            }
             jacobi_gram_kernel<<<dim3((unsigned)nsplit, (unsigned)n_cta), JTHREADS, jacobi_smem_bytes(), st>>>(
                 wf, d_mats, d_cta, d_rmap, round_counter, d_done, d_G);
             B200_CHECK_LAUNCH();
@@ -970,6 +1028,12 @@ extern "C" int b200_svd_set_eig_variant(int variant) {
 extern "C" int b200_svd_set_eig_inner_sweeps(int n) {
     int old = g_eig_inner_sweeps;
     if (n >= 0 && n <= 16) g_eig_inner_sweeps = n;   // 0: cross mode of version 3 (see jacobi_eig_kernel_v3)
+    return old;
+}
+
+extern "C" int b200_svd_set_fused_max_ld(int max_ld) {
+    int old = g_fused_max_ld;
+    if (max_ld >= 0) g_fused_max_ld = max_ld;
     return old;
 }
 

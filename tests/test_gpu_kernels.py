@@ -138,6 +138,41 @@ def test_block_svd_eig_variants(gpu_lib, eig_variant, shape):
     assert np.max(np.abs(VT @ VT.T - np.eye(k))) < 1e-12
 
 
+@pytest.mark.parametrize('inner', [2, 1, 0])
+@pytest.mark.parametrize('fused_ld', [0, 512])
+def test_block_svd_round_regimes(gpu_lib, inner, fused_ld):
+    """the two regimes of a Jacobi round -- three launches with column splits / one launch per round (small blocks) -- and the
+    modes of the pivot eigen-solver (2 or 1 inner sweeps, cross mode = 0) on a batch that mixes both block sizes"""
+    from tenpy_b200 import backend
+    rng = np.random.default_rng(21)
+    shapes = [(300, 260), (130, 400), (48, 48), (17, 5), (96, 31)]
+    mats = [rng.standard_normal(sh) * np.logspace(0, -6, sh[1])[None, :] for sh in shapes]
+    a_off, u_off, s_off, v_off = [], [], [], []
+    ao = uo = so = vo = 0
+    for (m, n) in shapes:
+        k = min(m, n)
+        a_off.append(ao), u_off.append(uo), s_off.append(so), v_off.append(vo)
+        ao, uo, so, vo = ao + m * n, uo + m * k, so + k, vo + k * n
+    dA = _dev(np.concatenate([a.ravel() for a in mats]))
+    dU, dS, dV = backend.zeros(uo), backend.zeros(so), backend.zeros(vo)
+    old_in, old_ld = gpu_lib.svd_set_eig_inner_sweeps(inner), gpu_lib.svd_set_fused_max_ld(fused_ld)
+    try:
+        info, nact, _ = gpu_lib.block_svd([s[0] for s in shapes], [s[1] for s in shapes], a_off, u_off, s_off, v_off, dA, dU, dS, dV)
+    finally:
+        gpu_lib.svd_set_eig_inner_sweeps(old_in)
+        gpu_lib.svd_set_fused_max_ld(old_ld)
+    U, S, V = backend.to_host(dU), backend.to_host(dS), backend.to_host(dV)
+    for (m, n), A, u, s_, v, na in zip(shapes, mats, u_off, s_off, v_off, nact):
+        k = min(m, n)
+        Ui, Si, Vi = U[u:u + m * k].reshape(m, k), S[s_:s_ + k], V[v:v + k * n].reshape(k, n)
+        Sref = np.linalg.svd(A, compute_uv=False)
+        assert na == k
+        assert np.max(np.abs(Si - Sref)) < 1e-12 * Sref[0]
+        assert np.max(np.abs(Ui @ np.diag(Si) @ Vi - A)) < 1e-12 * Sref[0]
+        assert np.max(np.abs(Ui.T @ Ui - np.eye(k))) < 1e-12
+        assert np.max(np.abs(Vi @ Vi.T - np.eye(k))) < 1e-12
+
+
 def test_block_svd_batch_graded(gpu_lib):
     """several blocks of different shapes in one batch, with strongly graded singular values"""
     from tenpy_b200 import backend
