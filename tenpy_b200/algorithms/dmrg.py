@@ -15,6 +15,7 @@ import time
 
 import numpy as np
 
+from .. import backend
 from ..linalg import np_conserved as npc
 from ..linalg.krylov_based import LanczosGroundState
 from ..linalg.truncation import svd_theta
@@ -22,6 +23,14 @@ from ..networks.mpo import MPOEnvironment
 from .mps_common import OneSiteH, TwoSiteH, DensityMatrixMixer, SubspaceExpansion, IdentityEnvRejected
 
 logger = logging.getLogger(__name__)
+
+
+class _PendingOverlap:
+    """<theta_guess|theta> left on the device by `diag` (resolved into ``update_stats['ov_change']`` at the end of the sweep)"""
+    __slots__ = ('dev',)
+
+    def __init__(self, dev):
+        self.dev = dev
 
 __all__ = ['run', 'TwoSiteDMRGEngine', 'SingleSiteDMRGEngine', 'chi_list', 'entropy', 'full_diag_effH']
 
@@ -152,6 +161,7 @@ class TwoSiteDMRGEngine:
                             'norm_err': []}
         self.shelve = False
         self.time0 = time.time()
+        self._pending_scalars = []       # (kind, index, 1-element device tensor): statistics read at the end of a sweep
 
     # ------------------------------------------------------------------ mixer
     def mixer_activate(self):
@@ -351,6 +361,7 @@ class TwoSiteDMRGEngine:
             self.update_env(**update_data)
             self.post_update_local(**update_data)
             self.free_no_longer_needed_envs()
+        self.resolve_pending_scalars()
         if optimize:
             self.sweeps += 1
             if self.mixer is not None:
@@ -360,6 +371,20 @@ class TwoSiteDMRGEngine:
                 else:
                     self.mixer = mixer
         return np.max(self.trunc_err_list)
+
+    def resolve_pending_scalars(self):
+        """read the statistics the bond updates left on the device (one transfer): overlaps -> ``update_stats['ov_change']``,
+        norms of the Lanczos results -> the reference's conditioning warning"""
+        pend, self._pending_scalars = self._pending_scalars, []
+        if not pend:
+            return
+        import torch
+        vals = backend.to_host(torch.cat([t for _, _, t in pend]))
+        for (kind, idx, _), v in zip(pend, vals):
+            if kind == 'ov':
+                self.update_stats['ov_change'][idx] = 1. - abs(float(v))
+            elif abs(1. - np.sqrt(v)) > 1.e-5:
+                logger.warning('poorly conditioned H matrix in KrylovBased! |psi_0| = %f', np.sqrt(v))
 
     def prepare_update_local(self):
         """Reference mps_common.py:498."""
@@ -397,10 +422,23 @@ class TwoSiteDMRGEngine:
                                               self.eff_H.N < self.options.get('max_N_for_ED', 400)):
             E, theta = full_diag_effH(self.eff_H, theta_guess, keep_sector=True)
         else:
+            lz = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params)
             try:
-                E, theta, N = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params).run()
+                E, theta, N = lz.run()
             except IdentityEnvRejected:      # the deferred test of the matvec shortcut failed: plain contraction order
-                E, theta, N = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params).run()
+                lz = LanczosGroundState(self.eff_H, theta_guess, self.lanczos_params)
+                E, theta, N = lz.run()
+            n2 = getattr(lz, '_result_norm2_dev', None)
+            if n2 is not None:               # conditioning test of the Lanczos result, read at the end of the sweep
+                self._pending_scalars.append(('norm2', None, n2))
+        # overlap of the new with the old wave function: a statistic only -- computed on the device now, read with all the
+        # others at the end of the sweep (no host round trip between the Lanczos result and the SVD)
+        if theta_guess._layout.nblocks and theta_guess._layout.same_blocks(theta._layout) and \
+                theta_guess.get_leg_labels() == theta.get_leg_labels() and np.all(theta_guess.qtotal == theta.qtotal):
+            lib = backend.get_lib()
+            ov = backend.empty(1)
+            lib.dot(theta._layout.size, theta_guess._buf, theta._buf, backend.dot_scratch(), ov)
+            return E, theta, N, _PendingOverlap(ov)
         ov_change = 1. - abs(npc.inner(theta_guess, theta, 'labels', do_conj=True))
         return E, theta, N, ov_change
 
@@ -480,6 +518,9 @@ class TwoSiteDMRGEngine:
         self.update_stats['E_trunc'].append(E_trunc)
         self.update_stats['N_lanczos'].append(N)
         self.update_stats['err'].append(err)
+        if isinstance(ov_change, _PendingOverlap):
+            self._pending_scalars.append(('ov', len(self.update_stats['ov_change']), ov_change.dev))
+            ov_change = np.nan
         self.update_stats['ov_change'].append(ov_change)
         self.update_stats['time'].append(time.time() - self.time0)
 

@@ -64,11 +64,32 @@ class KrylovBased:
             psif.iadd_prefactor_other(vf[N - k], self._cache[-k])
         self._cache = []
         self._rebuild_krylov_for_result_full(psif, N - len_cache - 1)
+        if getattr(self, 'device_scalars', False) and psif._layout.nblocks:
+            # normalisation without a host round trip (same arithmetic: |psi|^2 by the dot kernel, x *= 1 / sqrt(.)); the
+            # conditioning warning of the reference is raised when somebody reads `norm_check()` (the DMRG engine: at the
+            # end of the sweep)
+            lib = backend.get_lib()
+            n2 = backend.empty(1)
+            lib.dot(psif._layout.size, psif._buf, psif._buf, backend.dot_scratch(), n2)
+            lib.scal_rsqrt_dev(psif._layout.size, n2, psif._buf)
+            self._result_norm2_dev = n2
+            return psif
         psif_norm = npc.norm(psif)
         if abs(1. - psif_norm) > 1.e-5:
             logger.warning('poorly conditioned H matrix in KrylovBased! |psi_0| = %f', psif_norm)
         psif.iscale_prefactor(1. / psif_norm)
         return psif
+
+    def norm_check(self):
+        """the deferred conditioning test of :meth:`_calc_result_full` (synchronises); returns the norm or ``None``"""
+        n2 = getattr(self, '_result_norm2_dev', None)
+        if n2 is None:
+            return None
+        self._result_norm2_dev = None
+        psif_norm = float(np.sqrt(backend.read_scalar(n2)))
+        if abs(1. - psif_norm) > 1.e-5:
+            logger.warning('poorly conditioned H matrix in KrylovBased! |psi_0| = %f', psif_norm)
+        return psif_norm
 
 
 class LanczosGroundState(KrylovBased):
@@ -106,26 +127,27 @@ class LanczosGroundState(KrylovBased):
         h = self._h_krylov
         lib = backend.get_lib()
         w = self.psi0
-        beta0 = npc.norm(w)
-        if beta0 < self._cutoff:
-            raise ValueError('Norm of self.psi0 too small: {0!s}'.format(beta0))
-        if self._psi0_norm is None:
-            self._psi0_norm = beta0
-        sc = backend.zeros(2 * self.N_max)             # sc[2k] = alpha_k, sc[2k+1] = |w_k|^2 = beta_{k+1}^2
+        if w._layout.nblocks == 0:
+            raise ValueError('Norm of self.psi0 too small: 0.0')
+        # sc[2k] = alpha_k, sc[2k+1] = |w_k|^2 = beta_{k+1}^2; last entry: |psi0|^2 -- the start vector is normalised on the
+        # device as well (same arithmetic as `npc.norm` + `iscale_prefactor`), its norm is tested with the first chunk of
+        # scalars: no host round trip before the first `N_min` matvecs are enqueued
+        sc = backend.zeros(2 * self.N_max + 1)
+        nrm2_0 = sc[2 * self.N_max:2 * self.N_max + 1]
         scratch = backend.dot_scratch()
+        lib.dot(w._layout.size, w._buf, w._buf, scratch, nrm2_0)
         done_k = 0                                     # iterations whose scalars have been processed on the host
         k = 0
         while k < self.N_max:
             stop_at = self.N_min if k < self.N_min else min(self.N_max, k + self.sync_every)
             while k < stop_at:
-                if k == 0:
-                    w.iscale_prefactor(1. / beta0)
-                else:
-                    lib.scal_rsqrt_dev(w._layout.size, sc[2 * k - 1:2 * k], w._buf)
+                lib.scal_rsqrt_dev(w._layout.size, nrm2_0 if k == 0 else sc[2 * k - 1:2 * k], w._buf)
                 self._to_cache(w)
                 w = self.H.matvec(w)
                 v1 = self._cache[-1]
                 if not (w._layout is v1._layout or w._layout.same_blocks(v1._layout)):
+                    if self._psi0_norm is None:
+                        self._psi0_norm = float(np.sqrt(backend.read_scalar(nrm2_0)))
                     return None
                 lib.dot(w._layout.size, w._buf, v1._buf, scratch, sc[2 * k:2 * k + 1])
                 v0 = self._cache[-2]._buf if k > 0 else None
@@ -133,7 +155,13 @@ class LanczosGroundState(KrylovBased):
                                        sc[2 * k - 1:2 * k] if k > 0 else None, v0, w._buf, scratch,
                                        sc[2 * k + 1:2 * k + 2])
                 k += 1
-            vals = backend.to_host(sc[:2 * k])                        # the one synchronisation of this chunk
+            vals = backend.to_host(sc)                                # the one synchronisation of this chunk
+            if done_k == 0:
+                beta0 = float(np.sqrt(vals[-1]))
+                if not beta0 >= self._cutoff:
+                    raise ValueError('Norm of self.psi0 too small: {0!s}'.format(beta0))
+                if self._psi0_norm is None:
+                    self._psi0_norm = beta0
             check = getattr(self.H, 'deferred_check', None)
             if check is not None:
                 check()                                               # tests the operator postponed to this point
