@@ -968,7 +968,8 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
                 B200_CUDA_CHECK(cudaMemcpyAsync(d_mats, L.mats.data(), (size_t)nmat * sizeof(JMat), cudaMemcpyHostToDevice, st));
             if (remap)
                 B200_CUDA_CHECK(cudaMemcpyAsync(d_rmap, rmap.data(), rmap.size() * 4, cudaMemcpyHostToDevice, st));
-            B200_CUDA_CHECK(cudaStreamSynchronize(st));
+            // no synchronisation: the sources are pageable, i.e. staged by the driver before cudaMemcpyAsync returns, and
+            // the next sweep's kernels are ordered behind the copies on the stream
         }
     }
     (void)d_cta;
