@@ -10,6 +10,7 @@ for line in open('gpurun_out/r02r_svd_variants.jsonl'):
     d = json.loads(line)
     print(d['case'], {k: v for k, v in d.items() if k.endswith('_ms') or k.endswith('_sweeps')})
 PY
+timeout 300 python profiles/svd_gap_probe.py 40 1024 > $T/r02r_svd_gap.json 2> $T/r02r_svd_gap.err; cat $T/r02r_svd_gap.json | cut -c1-900; tail -c 300 $T/r02r_svd_gap.err
 for inner in 2 0 1; do
   B200_SVD_INNER=$inner timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-blocksparse > $T/r02r_tfi_in$inner.json 2> $T/r02r_tfi_in$inner.err
   python -c "

@@ -919,8 +919,11 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
         }
         jacobi_norms_kernel<<<dim3((unsigned)std::max(1, L.max_q), (unsigned)nmat), 128, 0, st>>>(wf, d_mats);
         B200_CHECK_LAUNCH();
+        auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_issued = debug ? now_ms() : 0.0;
         B200_CUDA_CHECK(cudaMemcpyAsync(rot.data(), d_rot, (size_t)nmat * 4, cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        const double t_synced = debug ? now_ms() : 0.0;
         bool changed = false, mats_changed = false, remap = false;
         long tot = 0;
         for (int i = 0; i < nmat; ++i) {
@@ -958,9 +961,6 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
             }
             remap = true;
         }
-        if (debug)
-            fprintf(stderr, "[jacobi] sweep %d: %ld rotated pairs, %d rounds, %d/%d matrices done, n_act[0]=%d/%d\n", sweep,
-                    tot, rounds, ndone, nmat, L.mats[0].n_act, L.mats[0].q);
         if (ndone < nmat) {
             if (changed)
                 B200_CUDA_CHECK(cudaMemcpyAsync(d_done, done.data(), (size_t)nmat * 4, cudaMemcpyHostToDevice, st));
@@ -971,6 +971,10 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
             // no synchronisation: the sources are pageable, i.e. staged by the driver before cudaMemcpyAsync returns, and
             // the next sweep's kernels are ordered behind the copies on the stream
         }
+        if (debug)   // host waited `wait` ms for the sweep's kernels; during `host gap` the GPU has nothing to do
+            fprintf(stderr, "[jacobi] sweep %d: %ld rotated pairs, %d rounds (%s), %d/%d matrices done, n_act[0]=%d/%d, wait %.3f ms, "
+                    "host gap %.3f ms\n", sweep, tot, rounds, fused ? "fused" : "split", ndone, nmat, L.mats[0].n_act, L.mats[0].q,
+                    t_synced - t_issued, now_ms() - t_synced);
     }
     (void)d_cta;
     return B200_OK;
