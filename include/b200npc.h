@@ -235,7 +235,7 @@ int b200_svd_set_eig_variant(int variant);
 int b200_svd_set_eig_inner_sweeps(int n);
 /* small-block regime of the block SVD / eigh: while the longest row (columns of Y, rows of W) of the matrices still being
  * iterated is <= max_ld, a Jacobi round is ONE launch (jacobi_round_fused_kernel: Gram matrix, pivot eigen-solver and
- * both applications back to back in the CTA of the pair) instead of three with column splits.  Default 512
+ * both applications back to back in the CTA of the pair) instead of three with column splits.  Default 256
  * (environment B200_SVD_FUSED_LD); 0 switches the regime off.  Returns the old value */
 int b200_svd_set_fused_max_ld(int max_ld);
 /* additional deflation threshold relative to |A_i|_F (default 0 = rounding level only): directions with a

@@ -696,6 +696,76 @@ __global__ void __launch_bounds__(128) jacobi_norms_kernel(double *__restrict__ 
     if (threadIdx.x == 0) work[mt.snorm_off + r] = sqrt(s);
 }
 
+// After a sweep, on the device: active-set bookkeeping of every matrix that is still iterating (one CTA per matrix).
+// Rows ordered by descending norm (ties by index: the order std::stable_sort gives), rows with norm <= defl behind the
+// active ones and out of the iteration; row map, nb_act, n_act updated in place, (nb_act, n_act) also to `act_out` for the
+// host's launch geometry.  q <= J_REORDER_MAX (bitonic sort in shared memory).
+constexpr int J_REORDER_MAX = 4096;
+__global__ void __launch_bounds__(256) jacobi_reorder_kernel(const double *__restrict__ work, JMat *mats, int *rmap,
+                                                             const int *__restrict__ done, const int *__restrict__ rot,
+                                                             int *__restrict__ act_out) {
+    extern __shared__ __align__(16) unsigned char rsm[];
+    __shared__ int s_nact;
+    const int mi = blockIdx.x, tid = threadIdx.x;
+    JMat &mt = mats[mi];
+    const int q = mt.q;
+    if (done[mi] || rot[mi] == 0 || !(mt.defl > 0.0)) {
+        if (tid == 0) {
+            act_out[2 * mi] = mt.nb_act;
+            act_out[2 * mi + 1] = mt.n_act;
+        }
+        return;
+    }
+    int np2 = 2;
+    while (np2 < q) np2 <<= 1;
+    double *key = reinterpret_cast<double *>(rsm);
+    int *idx = reinterpret_cast<int *>(rsm + (size_t)np2 * sizeof(double));
+    const double *nrm = work + mt.snorm_off;
+    for (int i = tid; i < np2; i += blockDim.x) {
+        key[i] = i < q ? nrm[i] : -1.0;       // padding sorts behind every real row (norms are >= 0)
+        idx[i] = i;
+    }
+    if (tid == 0) s_nact = 0;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const double ki = key[i], kl = key[l];
+                    const int ii = idx[i], il = idx[l];
+                    const bool i_first = ki > kl || (ki == kl && ii < il);     // i belongs before l in the final order
+                    const bool want_first = (i & k) == 0;
+                    if (i_first != want_first) {
+                        key[i] = kl;
+                        key[l] = ki;
+                        idx[i] = il;
+                        idx[l] = ii;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const double defl = mt.defl;
+    for (int i = tid; i < q; i += blockDim.x)
+        if (key[i] > defl && (i + 1 == q || !(key[i + 1] > defl))) s_nact = i + 1;
+    int *rm = rmap + mt.rmap_off;
+    for (int i = tid; i < mt.qp; i += blockDim.x) rm[i] = i < q ? idx[i] : i;
+    __syncthreads();
+    if (tid == 0) {
+        const int n_act = s_nact;
+        int nb_act = (n_act + JB - 1) / JB;
+        if (nb_act < 2) nb_act = 2;
+        if (nb_act & 1) ++nb_act;
+        if (nb_act > mt.nb) nb_act = mt.nb;
+        mt.nb_act = nb_act;
+        mt.n_act = n_act;
+        act_out[2 * mi] = nb_act;
+        act_out[2 * mi + 1] = n_act;
+    }
+}
+
 // SVD finalize: grid (max_k, nmat)
 __global__ void __launch_bounds__(128)
     svd_finalize_kernel(const double *__restrict__ work, const JMat *__restrict__ mats, const int *__restrict__ perm,
@@ -744,11 +814,11 @@ __global__ void __launch_bounds__(128)
 static int g_eig_variant = 3;
 static int env_fused_max_ld() {                     // B200_SVD_FUSED_LD: largest row length of the single-launch rounds (0: off)
     const char *e = getenv("B200_SVD_FUSED_LD");
-    if (e == nullptr || *e == 0) return 512;
+    if (e == nullptr || *e == 0) return 256;
     const int n = atoi(e);
-    return n >= 0 ? n : 512;
+    return n >= 0 ? n : 256;
 }
-static int g_fused_max_ld = env_fused_max_ld();
+static int g_fused_max_ld = env_fused_max_ld();   // measured (r02r): 39 blocks <= 250: 12.8 vs 14.1 ms; one 512^2 block: 26.3 vs 23.2 ms
 static int env_inner_sweeps() {                     // B200_SVD_INNER=0..16 overrides the default (A/B runs of whole sweeps)
     const char *e = getenv("B200_SVD_INNER");
     if (e == nullptr || *e == 0) return J_INNER_SWEEPS;
@@ -765,7 +835,7 @@ struct JLayout {
     int64_t off_flags = 0;
     int max_q = 0, max_nb = 0;
     // byte offsets of the integer regions inside the work buffer
-    int64_t off_mats = 0, off_cta = 0, off_rot = 0, off_done = 0, off_perm = 0, off_rmap = 0, total_bytes = 0;
+    int64_t off_mats = 0, off_cta = 0, off_rot = 0, off_done = 0, off_perm = 0, off_rmap = 0, off_act = 0, total_bytes = 0;
 };
 
 static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -833,6 +903,8 @@ static void make_layout(int64_t nblocks, const int64_t *m, const int64_t *n, boo
     b += rup(rmap * 4 + 4, 256);
     L.off_flags = b;
     b += rup((int64_t)L.cta_mat.size() * 4 + 4, 256);
+    L.off_act = b;                     // (nb_act, n_act) per matrix, written by jacobi_reorder_kernel
+    b += rup(nblocks * 8, 256);
     L.total_bytes = b;
 }
 
@@ -876,6 +948,11 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
     B200_CUDA_CHECK(cudaMemsetAsync(d_done, 0, (size_t)nmat * 4, st));
     int ndone = 0;
     int round_counter = 0;
+    // active-set bookkeeping between the sweeps on the device (jacobi_reorder_kernel) unless a matrix is too large for its
+    // shared-memory sort or B200_SVD_HOST_REORDER is set (A/B): then row norms come back to the host, one copy per matrix
+    const bool dev_reorder = L.max_q <= J_REORDER_MAX && getenv("B200_SVD_HOST_REORDER") == nullptr;
+    int *d_act = reinterpret_cast<int *>(work + L.off_act);
+    std::vector<int> act((size_t)2 * nmat, 0);
     std::vector<double> nrm;
     std::vector<int> order;
     for (int sweep = 0; sweep < max_sweeps && ndone < nmat; ++sweep) {
@@ -920,6 +997,13 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
         jacobi_norms_kernel<<<dim3((unsigned)std::max(1, L.max_q), (unsigned)nmat), 128, 0, st>>>(wf, d_mats);
         B200_CHECK_LAUNCH();
         auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        if (dev_reorder) {
+            int np2 = 2;
+            while (np2 < L.max_q) np2 <<= 1;
+            jacobi_reorder_kernel<<<nmat, 256, (size_t)np2 * 12, st>>>(wf, d_mats, d_rmap, d_done, d_rot, d_act);
+            B200_CHECK_LAUNCH();
+            B200_CUDA_CHECK(cudaMemcpyAsync(act.data(), d_act, (size_t)nmat * 8, cudaMemcpyDeviceToHost, st));
+        }
         const double t_issued = debug ? now_ms() : 0.0;
         B200_CUDA_CHECK(cudaMemcpyAsync(rot.data(), d_rot, (size_t)nmat * 4, cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -938,6 +1022,11 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
                 continue;
             }
             if (mt.defl <= 0.0) continue;
+            if (dev_reorder) {        // the device has re-ordered the rows and updated its descriptors: mirror the geometry
+                mt.nb_act = act[(size_t)2 * i];
+                mt.n_act = act[(size_t)2 * i + 1];
+                continue;
+            }
             // re-order the logical rows: active rows by descending norm, then the deflated ones
             nrm.resize((size_t)mt.q);
             B200_CUDA_CHECK(cudaMemcpy(nrm.data(), wf + mt.snorm_off, (size_t)mt.q * sizeof(double), cudaMemcpyDeviceToHost));
