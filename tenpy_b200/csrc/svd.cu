@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(128) jacobi_norms_kernel(double *__restrict__ 
 // active ones and out of the iteration; row map, nb_act, n_act updated in place, (nb_act, n_act) also to `act_out` for the
 // host's launch geometry.  q <= J_REORDER_MAX (bitonic sort in shared memory).
 constexpr int J_REORDER_MAX = 4096;
-__global__ void __launch_bounds__(256) jacobi_reorder_kernel(const double *__restrict__ work, JMat *mats, int *rmap,
+__global__ void __launch_bounds__(1024) jacobi_reorder_kernel(const double *__restrict__ work, JMat *mats, int *rmap,
                                                              const int *__restrict__ done, const int *__restrict__ rot,
                                                              int *__restrict__ act_out) {
     extern __shared__ __align__(16) unsigned char rsm[];
@@ -1000,7 +1000,7 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
         if (dev_reorder) {
             int np2 = 2;
             while (np2 < L.max_q) np2 <<= 1;
-            jacobi_reorder_kernel<<<nmat, 256, (size_t)np2 * 12, st>>>(wf, d_mats, d_rmap, d_done, d_rot, d_act);
+            jacobi_reorder_kernel<<<nmat, std::max(64, std::min(1024, np2 / 2)), (size_t)np2 * 12, st>>>(wf, d_mats, d_rmap, d_done, d_rot, d_act);
             B200_CHECK_LAUNCH();
             B200_CUDA_CHECK(cudaMemcpyAsync(act.data(), d_act, (size_t)nmat * 8, cudaMemcpyDeviceToHost, st));
         }
