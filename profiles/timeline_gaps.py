@@ -22,9 +22,10 @@ from tenpy_b200.models import TFIChain  # noqa: E402
 
 
 def short(name):
+    name = name.replace('(anonymous namespace)::', '').replace('<unnamed>::', '')
     name = re.sub(r'\(.*', '', name)
     name = re.sub(r'<.*', '', name)
-    return name.split('::')[-1][:40]
+    return name.split('::')[-1].strip()[:40] or 'anonymous'
 
 
 def main():
