@@ -932,6 +932,9 @@ static int run_jacobi(JLayout &L, char *work, cudaStream_t st, int32_t *info, in
                                              jacobi_smem_bytes()));
         B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              jacobi_smem_bytes()));
+        // (q = 4096: 48 KB of keys and indices + the kernel's static shared memory is above the default limit)
+        B200_CUDA_CHECK(cudaFuncSetAttribute(jacobi_reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             J_REORDER_MAX * 12));
         attr_set = true;
     }
     std::vector<int> rot((size_t)nmat), done((size_t)nmat, 0);

@@ -167,10 +167,16 @@ class LanczosGroundState(KrylovBased):
                 check()                                               # tests the operator postponed to this point
             for kk in range(done_k, k):
                 h[kk, kk] = vals[2 * kk]
-                self._calc_result_krylov(kk)
+                # the tridiagonal eigen-problem of step kk is needed for the convergence test of steps kk and kk + 1 (which
+                # can only trigger from step N_min - 1 on) and for the result: skipped for the first N_min - 2 steps
+                solved = kk + 2 >= self.N_min
+                if solved:
+                    self._calc_result_krylov(kk)
                 beta = float(np.sqrt(vals[2 * kk + 1]))
                 h[kk, kk + 1] = h[kk + 1, kk] = beta
                 if not np.isfinite(beta) or abs(beta) < self._cutoff or (kk + 1 >= self.N_min and self._converged(kk)):
+                    if not solved:
+                        self._calc_result_krylov(kk)
                     for _ in range(k - (kk + 1)):                     # vectors of the discarded iterations
                         self._cache.pop()
                     return kk + 1

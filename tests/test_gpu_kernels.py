@@ -173,6 +173,32 @@ def test_block_svd_round_regimes(gpu_lib, inner, fused_ld):
         assert np.max(np.abs(Vi @ Vi.T - np.eye(k))) < 1e-12
 
 
+def test_block_svd_4096_rows_active_set(gpu_lib):
+    """q = 4096 vectors (the two-site wave function at chi = 2048): the device-side active-set bookkeeping sorts 4096 row
+    norms in shared memory (48 KB + the kernel's static shared memory: opt-in limit); numerically low-rank input"""
+    from tenpy_b200 import backend
+    rng = np.random.default_rng(8)
+    n, r = 4096, 40
+    q1, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    q2, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    sv = np.logspace(0, -6, r)
+    A = (q1 * sv) @ q2.T
+    dA = _dev(A.ravel())
+    dU, dS, dV = backend.zeros(n * n), backend.zeros(n), backend.zeros(n * n)
+    old = gpu_lib.svd_set_deflation_tol(1e-10)
+    try:
+        info, nact, _ = gpu_lib.block_svd([n], [n], [0], [0], [0], [0], dA, dU, dS, dV)
+    finally:
+        gpu_lib.svd_set_deflation_tol(old)
+    S = backend.to_host(dS)
+    assert info[0] > 0 and r <= nact[0] < 200
+    assert np.max(np.abs(S[:r] - sv)) < 1e-12
+    U = backend.to_host(dU).reshape(n, n)[:, :r]
+    VT = backend.to_host(dV).reshape(n, n)[:r]
+    assert np.max(np.abs((U * S[:r]) @ VT - A)) < 1e-9
+    assert np.max(np.abs(U.T @ U - np.eye(r))) < 1e-12
+
+
 def test_block_svd_batch_graded(gpu_lib):
     """several blocks of different shapes in one batch, with strongly graded singular values"""
     from tenpy_b200 import backend
