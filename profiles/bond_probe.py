@@ -33,7 +33,7 @@ model = TFIChain({'L': L, 'J': 1., 'g': 1., 'conserve': None})
 psi = bench.synthetic_mps(model, L, chi, 2, seed=0)
 eng = dmrg.TwoSiteDMRGEngine(psi, model, {
     'mixer': None, 'combine': True, 'diag_method': 'lanczos', 'svd_warm_start': False,
-    'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None},
+    'trunc_params': {'chi_max': chi, 'svd_min': 1e-45, 'trunc_cut': None, 'svd_deflation_tol': 1e-10},   # as bench.py
     'lanczos_params': {'N_min': args.lanczos_N, 'N_max': args.lanczos_N}})
 for _ in range(args.warm_sweeps):
     eng.sweep()

@@ -209,11 +209,14 @@ def svd_theta(theta, trunc_par, qtotal_LR=[None, None], inner_labels=['vR', 'vL'
     if res is not None:
         U, S, VH, lost = res
     else:
-        # how many singular triplets the truncation below can keep at most: chi_max; none of the deflated directions (values
-        # <= tol |theta|) if they are below `svd_min` anyway -- then their vectors need no orthonormal completion
+        # how many singular triplets the truncation below can keep at most: chi_max; none of the deflated directions if they
+        # are below `svd_min` anyway -- then their vectors need no orthonormal completion.  Deflated = values below
+        # max(tol, rounding level) |theta|; the rounding-level threshold of the kernel is 16 eps sqrt(max(m, n)) per block
+        # (1.6e-13 for 2048 columns), bounded here by 1e-11: a smaller `svd_min` may keep such directions (LAPACK reports
+        # them as ~1e-17 |theta|, the reference's truncation keeps them down to svd_min) and they are completed
         n_keep = chi_max
         svd_min, chi_min = trunc_par.get('svd_min', 1.e-14), trunc_par.get('chi_min', None)
-        if svd_min and 0. < tol <= svd_min and not (chi_min and chi_min > 1):
+        if svd_min and svd_min >= max(tol, 1.e-11) and not (chi_min and chi_min > 1):
             n_keep = 0
         U, S, VH = npc.svd(theta, full_matrices=False, compute_uv=True, qtotal_LR=qtotal_LR,
                            inner_labels=inner_labels, guess=guess, deflation_tol=tol,
