@@ -378,6 +378,24 @@ def test_lanczos_device_scalars(fake_device):
     assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
 
 
+def test_sweep_resolves_device_statistics(fake_device):
+    """the overlap statistic and the norm of the Lanczos result stay on the device during a sweep (no host round trip between
+    the eigensolver and the SVD); `sweep` reads them in one transfer: `update_stats['ov_change']` holds numbers afterwards"""
+    from tenpy_b200.models import TFIChain
+    from tenpy_b200.networks.mps import MPS
+    from tenpy_b200.algorithms import dmrg
+    M = TFIChain({'L': 8, 'J': 1., 'g': 1.2, 'conserve': None})
+    psi = MPS.from_product_state(M.lat_sites, ['up'] * 8)
+    eng = dmrg.TwoSiteDMRGEngine(psi, M, {'mixer': None, 'combine': True, 'diag_method': 'lanczos',
+                                           'trunc_params': {'chi_max': 16, 'svd_min': 1e-12}})
+    eng.sweep()
+    eng.sweep()
+    ov = np.array(eng.update_stats['ov_change'], dtype=float)
+    assert len(ov) == 2 * 2 * (8 - 2) and np.all(np.isfinite(ov)) and np.all(ov > -1e-12) and np.all(ov <= 1. + 1e-12)
+    assert ov[-1] < 1e-6                      # converged: the last update hardly changes the wave function
+    assert eng._pending_scalars == []
+
+
 def test_split_matvec_shares_buffers_without_charges(fake_device):
     """the split-order matvec relabels instead of copying when combining / splitting is the identity on the packed buffer
     (no charges): no block-move launch for the theta reshapes, input untouched, result owns its buffer"""
