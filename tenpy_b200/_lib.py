@@ -92,6 +92,7 @@ TAKE_REC = 7
 SCALE_REC = 5
 DOT_SCRATCH = 2048
 BLOCK_ALIGN = 16
+B200_ERR_NOCONV = 3      # include/b200npc.h
 
 
 class B200Error(RuntimeError):
@@ -215,6 +216,7 @@ class DeviceLib:
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.profile = None   # set to {} to collect CUDA-event timings per kernel family
         self._stream = None
+        self.noconv_retries = 0   # block SVD batches repeated with the conservative settings after B200_ERR_NOCONV
 
     def profile_summary(self):
         """{family: (n_calls, total_ms)} of the collected event pairs; synchronises."""
@@ -373,11 +375,25 @@ class DeviceLib:
         info = np.zeros(nb, dtype=np.int32)
         nact = np.zeros(nb, dtype=np.int32)
         transp = np.zeros(nb, dtype=np.int32)
+        def call():
+            return self.c.b200_block_svd_f64(nb, ms[1], ns[1], ao[1], uo[1], so[1], vo[1], _ptr(A), _ptr(U), _ptr(S), _ptr(VT),
+                                             _ptr(work), wbytes, info.ctypes.data_as(c_i32p), nact.ctypes.data_as(c_i32p),
+                                             transp.ctypes.data_as(c_i32p), self.stream())
         with _Prof(self, 'svd'):
-            self._check(self.c.b200_block_svd_f64(nb, ms[1], ns[1], ao[1], uo[1], so[1], vo[1], _ptr(A), _ptr(U),
-                                                  _ptr(S), _ptr(VT), _ptr(work), wbytes, info.ctypes.data_as(c_i32p),
-                                                  nact.ctypes.data_as(c_i32p), transp.ctypes.data_as(c_i32p),
-                                                  self.stream()))
+            rc = call()
+            if rc == B200_ERR_NOCONV:
+                # a block did not converge within the sweep limit: once more with the conservative settings (four inner
+                # sweeps of the pivot solver, every direction iterated to convergence) before giving up; A is untouched
+                self.noconv_retries += 1
+                old_in, old_defl = self.svd_set_eig_inner_sweeps(4), self.svd_set_deflation(False)
+                try:
+                    U.zero_()
+                    VT.zero_()
+                    rc = call()
+                finally:
+                    self.svd_set_eig_inner_sweeps(old_in)
+                    self.svd_set_deflation(old_defl)
+            self._check(rc)
         return info, nact, transp
 
     def block_qr(self, m, n, a_off, q_off, r_off, A, Q, R):
@@ -401,7 +417,7 @@ class DeviceLib:
         return float(self.c.b200_svd_set_deflation_tol(float(tol_rel)))
 
     def svd_set_eig_inner_sweeps(self, n):
-        """inner sweeps of jacobi_eig_kernel_v2 (default 4); returns the old value"""
+        """inner sweeps of the version-3 pivot eigen-solver (default 2; 0 = cross mode); returns the old value"""
         return int(self.c.b200_svd_set_eig_inner_sweeps(int(n)))
 
     def svd_set_fused_max_ld(self, max_ld):

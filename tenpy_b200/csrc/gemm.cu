@@ -657,21 +657,27 @@ extern "C" int b200_grouped_gemm_f64(int64_t n_tasks, const int64_t *m, const in
                                      const int64_t *b_off, const double *A, const double *B, double *C,
                                      b200_stream_t stream) {
     if (n_tasks <= 0) return B200_OK;
+    if (pair_ptr[n_tasks] > n_pairs) return set_error(B200_ERR_ARG, "grouped_gemm: pair_ptr exceeds n_pairs");
     std::vector<GemmTask> tasks((size_t)n_tasks);
-    std::vector<GemmPair> pairs((size_t)n_pairs);
+    std::vector<GemmPair> pairs;
+    pairs.reserve((size_t)n_pairs);
     for (int64_t t = 0; t < n_tasks; ++t) {
         tasks[t].c_off = c_off[t];
         tasks[t].m = (int32_t)m[t];
         tasks[t].n = (int32_t)n[t];
-        tasks[t].pair_begin = (int32_t)pair_ptr[t];
-        tasks[t].pair_end = (int32_t)pair_ptr[t + 1];
+        tasks[t].pair_begin = (int32_t)pairs.size();
+        for (int64_t p = pair_ptr[t]; p < pair_ptr[t + 1]; ++p) {
+            if (k[p] <= 0) continue;   // an empty product contributes nothing (and must not take a pipeline stage)
+            GemmPair pr;
+            pr.a_off = a_off[p];
+            pr.b_off = b_off[p];
+            pr.k = (int32_t)k[p];
+            pr.pad = 0;
+            pairs.push_back(pr);
+        }
+        tasks[t].pair_end = (int32_t)pairs.size();   // a task without products writes a zero block
     }
-    for (int64_t p = 0; p < n_pairs; ++p) {
-        pairs[p].a_off = a_off[p];
-        pairs[p].b_off = b_off[p];
-        pairs[p].k = (int32_t)k[p];
-        pairs[p].pad = 0;
-    }
+    if (pairs.empty()) pairs.push_back(GemmPair{0, 0, 0, 0});   // (never dereferenced by a k-step; keeps the copies below non-empty)
     // descriptors go to a persistent grow-only device scratch (no cudaMalloc/cudaFree per call)
     static char *scratch = nullptr;
     static size_t scratch_cap = 0;

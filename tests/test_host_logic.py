@@ -378,6 +378,56 @@ def test_lanczos_device_scalars(fake_device):
     assert np.max(np.abs(psi.entanglement_entropy() - g['tfi_S'])) < 1e-8
 
 
+def test_block_svd_retries_once_after_noconv():
+    """binding logic: B200_ERR_NOCONV of the block SVD is answered by ONE repetition with the conservative settings (four
+    inner sweeps of the pivot solver, no deflation, zeroed outputs), the library state is restored, a second failure raises"""
+    import torch
+    from tenpy_b200 import _lib
+
+    class FakeC:
+        def __init__(self, rcs):
+            self.rcs, self.calls, self.state, self.log = list(rcs), 0, {'inner': 2, 'defl': 1}, []
+
+        def b200_block_svd_worksize(self, nb, m, n):
+            return 64
+
+        def b200_block_svd_f64(self, *a):
+            self.calls += 1
+            self.log.append(dict(self.state))
+            return self.rcs.pop(0)
+
+        def b200_svd_set_eig_inner_sweeps(self, n):
+            old, self.state['inner'] = self.state['inner'], n
+            return old
+
+        def b200_svd_set_deflation(self, on):
+            old, self.state['defl'] = self.state['defl'], on
+            return old
+
+        def b200_last_error(self):
+            return b'block Jacobi SVD did not converge'
+
+    def make(rcs):
+        lib = object.__new__(_lib.DeviceLib)
+        lib.torch, lib.c, lib.device, lib.profile, lib._stream, lib.noconv_retries = torch, FakeC(rcs), torch.device('cpu'), None, \
+            _lib.c_vp(0), 0
+        return lib
+    A, U, S, VT = torch.ones(4, dtype=torch.float64), torch.ones(4, dtype=torch.float64), torch.zeros(2, dtype=torch.float64), \
+        torch.ones(4, dtype=torch.float64)
+    lib = make([_lib.B200_ERR_NOCONV, 0])
+    lib.block_svd([2], [2], [0], [0], [0], [0], A, U, S, VT)
+    assert lib.c.calls == 2 and lib.noconv_retries == 1
+    assert lib.c.log == [{'inner': 2, 'defl': 1}, {'inner': 4, 'defl': 0}] and lib.c.state == {'inner': 2, 'defl': 1}
+    assert float(U.abs().sum()) == 0. and float(VT.abs().sum()) == 0. and float(A.sum()) == 4.
+    lib = make([_lib.B200_ERR_NOCONV, _lib.B200_ERR_NOCONV])
+    with pytest.raises(_lib.B200Error):
+        lib.block_svd([2], [2], [0], [0], [0], [0], A, U, S, VT)
+    assert lib.c.calls == 2 and lib.c.state == {'inner': 2, 'defl': 1}
+    lib = make([0])
+    lib.block_svd([2], [2], [0], [0], [0], [0], A, U, S, VT)
+    assert lib.c.calls == 1 and lib.noconv_retries == 0
+
+
 def test_sweep_resolves_device_statistics(fake_device):
     """the overlap statistic and the norm of the Lanczos result stay on the device during a sweep (no host round trip between
     the eigensolver and the SVD); `sweep` reads them in one transfer: `update_stats['ov_change']` holds numbers afterwards"""
