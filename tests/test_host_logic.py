@@ -428,6 +428,36 @@ def test_block_svd_retries_once_after_noconv():
     assert lib.c.calls == 1 and lib.noconv_retries == 0
 
 
+def test_svd_theta_completes_only_what_the_truncation_can_keep(fake_device):
+    """numerically rank-deficient theta: the directions the SVD kernel deflates get an orthonormal completion only if the
+    truncation could keep them -- not with svd_min above the deflation threshold (they are cut: zero vectors, S = 0), but with
+    a tiny svd_min (the benchmark harness: 1e-45), where the reference keeps LAPACK's ~1e-17 values and chi stays at chi_max"""
+    from tenpy_b200.linalg import np_conserved as npc
+    from tenpy_b200.linalg.truncation import svd_theta
+    rng = np.random.default_rng(3)
+    n, r = 24, 5
+    q1, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    q2, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    A = (q1 * np.logspace(0, -3, r)) @ q2.T
+    ci = npc.ChargeInfo()
+    legs = [npc.LegCharge.from_trivial(n, ci, +1), npc.LegCharge.from_trivial(n, ci, -1)]
+
+    def run(trunc):
+        theta = npc.Array.from_ndarray(A, legs, labels=['(vL.p0)', '(p1.vR)'])
+        before = fake_device.calls.get('col_sqnorms', 0)          # the leverage scores: first step of every completion
+        U, S, VH, err, renorm = svd_theta(theta, trunc)
+        return U, S, VH, fake_device.calls.get('col_sqnorms', 0) - before
+    U, S, VH, completed = run({'chi_max': 16, 'svd_min': 1e-10})
+    assert completed == 0 and len(S) == r
+    assert np.max(np.abs(npc.tensordot(U.scale_axis(S, 1), VH, axes=1).to_ndarray() * np.linalg.norm(A) - A)) < 1e-12
+    U, S, VH, completed = run({'chi_max': 16, 'svd_min': 1e-45, 'trunc_cut': None, 'svd_deflation_tol': 1e-10})
+    assert completed == 1 and len(S) == 16
+    u, vh = U.to_ndarray(), VH.to_ndarray()
+    assert np.max(np.abs(u.T @ u - np.eye(16))) < 1e-12 and np.max(np.abs(vh @ vh.T - np.eye(16))) < 1e-12
+    U, S, VH, completed = run({'chi_max': 16, 'svd_min': 1e-14})      # below the rounding-level threshold: completed as well
+    assert completed == 1
+
+
 def test_sweep_resolves_device_statistics(fake_device):
     """the overlap statistic and the norm of the Lanczos result stay on the device during a sweep (no host round trip between
     the eigensolver and the SVD); `sweep` reads them in one transfer: `update_stats['ov_change']` holds numbers afterwards"""
