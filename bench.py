@@ -454,6 +454,9 @@ def workload_config(args, n):
                             "4 D d^2 chi^3 flop instead of the reference default's 4 D d^3 chi^3; same result); the "
                             "identity components LP[IdL] = RP[IdR] = 1 of the environments (checked per bond) are not "
                             "multiplied: 4 (D-1) d^2 chi^3 flop in the two large GEMMs",
+            'svd': 'b200 arm: block Jacobi SVD with svd_deflation_tol=1e-10 (directions below 1e-10 |theta| are not iterated to '
+                   'convergence; they get an orthonormal completion because svd_min=1e-45 keeps them, as the reference keeps '
+                   "LAPACK's ~1e-17 values); reference arm: LAPACK gesdd",
             'parallelism': 'independent DMRG runs (field scan g=1+0.02*rank), %d rank(s)' % n,
             'l2': 'working set per step (100 x (LP, RP, B) ~ 7 GB) >> 126 MB L2; no explicit flush'}
 
