@@ -742,7 +742,7 @@ def run_b200(args):
 
 def run_chi_scan(args, lib, world, rank):
     """BASELINE.json configs[4]: 8 independent DMRG runs, chi in {256, 512, 1024, 2048} x g in {0.9, 1.1}, sharded over the
-    ranks with `tenpy_b200.scan` (largest estimated cost chi^3 first, always to the least loaded rank).  Each run = the
+    ranks with `tenpy_b200.scan` (largest estimated cost chi^3 first; every rank pulls its next run when it becomes free).  Each run = the
     benchmark's workload at its own chi: synthetic state, one warm-up sweep, one timed sweep (CUDA events).  Returns on
     rank 0 the per-run table, the per-rank busy times and the load-balance efficiency (mean / max rank time)."""
     import torch
@@ -778,7 +778,8 @@ def run_chi_scan(args, lib, world, rank):
                      for r in table],
             'rank_busy_s': per_rank, 'makespan_s': max(per_rank),
             'load_balance_efficiency': float(np.mean(per_rank) / max(per_rank)) if max(per_rank) > 0 else None,
-            'assignment': 'LPT on chi^3 (tenpy_b200.scan.assign_runs)', 'sweeps_per_run': '1 warm-up + 1 timed'}
+            'assignment': 'runs ordered by chi^3, pulled by the ranks from a shared counter as they become free (tenpy_b200.scan.run_scan, '
+                          "schedule='dynamic'; static LPT on chi^3 if the ranks share no store)", 'sweeps_per_run': '1 warm-up + 1 timed'}
 
 
 def _matvec_gflops(mv_orders):
