@@ -4,6 +4,8 @@ point operation on the hot path is a kernel of ``libb200npc.so`` reached through
 """
 # Copyright (C) 2026 tenpy_b200 authors. Apache-2.0.
 
+import os
+
 import numpy as np
 import torch
 
@@ -55,14 +57,34 @@ def zeros(n):
     return torch.zeros(int(n), dtype=torch.float64, device=get_lib().device)
 
 
+PIN_MAX_BYTES = 1 << 20
+_BLOCKING_H2D = bool(os.environ.get('B200_BLOCKING_H2D'))     # A/B switch: the blocking uploads of rounds 1 / 2
+
+
 def to_device(a, pin=False):
-    """numpy array (float64 / int64 / int32) -> device tensor."""
+    """numpy array (float64 / int64 / int32) -> device tensor, WITHOUT synchronising the stream.
+
+    A blocking ``tensor.to(device)`` from pageable memory ends in a stream synchronisation (ATen's copy kernel), and the
+    engine uploads ~10 small arrays per bond update (index records, Schmidt values for `scale_axis`, ...): each one made the
+    host wait for everything the GPU had queued, i.e. the host could never run ahead of the device across such a call.
+    Small arrays go through torch's caching pinned-memory allocator (the copy is asynchronous, the pinned block is recycled
+    after the copy has run); large ones (MPS tensors at set-up) are copied from pageable memory without the final
+    synchronisation (the driver stages the source before `cudaMemcpyAsync` returns).  Stream order makes every later kernel
+    see the data."""
     a = np.ascontiguousarray(a)
     t = torch.from_numpy(a)
     dev = get_lib().device
     if dev.type == 'cpu':
         return t.clone()
-    return t.to(dev)
+    if t.numel() == 0:
+        return torch.empty(t.shape, dtype=t.dtype, device=dev)
+    if _BLOCKING_H2D:
+        return t.to(dev)
+    try:
+        src = t.pin_memory() if (pin or t.numel() * t.element_size() <= PIN_MAX_BYTES) else t
+        return src.to(dev, non_blocking=True)
+    except RuntimeError:          # no pinned memory to be had: the blocking copy is always available
+        return t.to(dev)
 
 
 def to_host(t):
